@@ -1,0 +1,530 @@
+"""CPU oracle for the GP hot path of helgeanl/GP-MPC  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy/LAPACK restatement of the reference's dense GP regression
+path.  It is the checker, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  Nothing under ``gp-mpc_b200/`` imports it.
+
+Pinning status ("how do we know the oracle is right"):
+  * The reference has NO tests; its only result-pinning artifacts are the two
+    saved models ``examples/models/gp_{tank,car}_example.json``.  This oracle
+    reproduces their stored ``chol`` / ``alpha`` / ``invK`` from the stored
+    ``(X, Y, hyper)`` (``tests/test_oracle_golden.py``).
+  * The reference's numpy-only functions (``optimize.calc_cov_matrix``,
+    ``optimize.calc_NLL_numpy``, ``GP.covSEard``, ``GP.covar``) were imported
+    VERBATIM in the build container (casadi/pyDOE/matplotlib stubbed, see
+    ``oracle/ref_loader.py``) and their outputs on the fixtures are committed
+    under ``tests/golden/`` by ``oracle/make_golden.py``; this oracle is checked
+    against them.
+  * The CasADi-only graph builders (``build_gp``, ``build_TA_cov``,
+    ``gp_exact_moment``) cannot run here (CasADi, unpinned "tested with 3.4",
+    README.md:21, is absent).  They are restated below following the cited
+    lines; that part is "parity unpinned by reference execution" and is
+    cross-checked by finite differences and limiting cases instead.
+
+All citations are ``file:line`` relative to the reference checkout.
+Arithmetic is fp64 throughout.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:  # scipy is only needed for the triangular solves / SLSQP driver
+    from scipy.linalg import solve_triangular as _solve_tri
+except Exception:  # pragma: no cover
+    _solve_tri = None
+
+
+# ----------------------------------------------------------------------------
+# a1  ARD squared-exponential kernel
+# ----------------------------------------------------------------------------
+def covSEard(X, Z, ell, sf2):
+    """k(x,z) = sf2 * exp(-1/2 sum_d (x_d - z_d)^2 / ell_d^2), direct differences.
+
+    Follows the CasADi kernel ``gp_functions.py:17-22`` (``(x - z)**2 / ell**2``
+    summed, then one exp).  X:(n1,D)  Z:(n2,D)  ->  (n1,n2).
+    """
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+    ell = np.asarray(ell, dtype=np.float64).reshape(-1)
+    if X.shape[1] != Z.shape[1]:
+        # same error behaviour as GP.covSEard, gp_class.py:342-344
+        raise ValueError('Input dimensions are not the same! D_x=' + str(X.shape[1])
+                         + ', D_z=' + str(Z.shape[1]))
+    dist = np.zeros((X.shape[0], Z.shape[0]))
+    for d in range(X.shape[1]):
+        diff = X[:, d][:, None] - Z[:, d][None, :]
+        dist += diff * diff / ell[d] ** 2
+    return sf2 * np.exp(-0.5 * dist)
+
+
+def covSEard_expanded(X, Z, ell, sf2):
+    """Same kernel through the a^2 + b^2 - 2ab expansion per dimension.
+
+    Follows the numeric twins ``optimize.py:303-319`` (``calc_cov_matrix``) and
+    ``gp_class.py:345-350`` (``GP.covSEard``): per dimension
+    ``(sum(x1**2) + sum(x2**2) - 2 x1 x2^T) / ell_i**2`` accumulated, one exp.
+    """
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+    dist = 0
+    n1, n2 = X.shape[0], Z.shape[0]
+    for i in range(X.shape[1]):
+        x1 = X[:, i].reshape(n1, 1)
+        x2 = Z[:, i].reshape(n2, 1)
+        dist = (np.sum(x1 ** 2, 1).reshape(-1, 1) + np.sum(x2 ** 2, 1)
+                - 2 * np.dot(x1, x2.T)) / ell[i] ** 2 + dist
+    return sf2 * np.exp(-.5 * dist)
+
+
+def calc_cov_matrix(X, ell, sf2):
+    """``optimize.py:303-319``: K(X,X) without noise (expansion form)."""
+    return covSEard_expanded(X, X, ell, sf2)
+
+
+# ----------------------------------------------------------------------------
+# a2/a3  K assembly + Cholesky with the single 1e-8 jitter retry
+# ----------------------------------------------------------------------------
+def assemble_K(X, hyper_a):
+    """``optimize.py:338-344`` / ``:476-482``: K = k(X,X) + sn2 I, symmetrised."""
+    X = np.asarray(X, dtype=np.float64)
+    n, D = X.shape
+    ell = hyper_a[:D]
+    sf2 = hyper_a[D] ** 2
+    sn2 = hyper_a[D + 1] ** 2
+    K = calc_cov_matrix(X, ell, sf2)
+    K = K + sn2 * np.eye(n)
+    K = (K + K.T) * 0.5
+    return K
+
+
+def chol_with_jitter(K, jitter=1e-8):
+    """``optimize.py:345-350`` (= ``:483-488``, ``gp_class.py:524-529``).
+
+    Returns (L, jitter_used).  A second failure propagates LinAlgError like the
+    reference does.
+    """
+    try:
+        return np.linalg.cholesky(K), False
+    except np.linalg.LinAlgError:
+        K = K + np.eye(K.shape[0]) * jitter
+        return np.linalg.cholesky(K), True
+
+
+# ----------------------------------------------------------------------------
+# a4-a6  NLML (no N/2 log 2pi term, zero mean only)
+# ----------------------------------------------------------------------------
+def calc_NLL(hyper_a, X, y, lapack_general_solve=True):
+    """``optimize.py:322-356`` (``calc_NLL_numpy``).
+
+    ``lapack_general_solve=True`` reproduces the reference's use of
+    ``np.linalg.solve`` (general LU) on the triangular factor (``:353-354``);
+    False uses true triangular solves (results agree to rounding).
+    """
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    K = assemble_K(X, np.asarray(hyper_a, dtype=np.float64))
+    L, _ = chol_with_jitter(K)
+    logK = 2 * np.sum(np.log(np.abs(np.diag(L))))            # :352
+    if lapack_general_solve or _solve_tri is None:
+        invLy = np.linalg.solve(L, y)                        # :353
+        alpha = np.linalg.solve(L.T, invLy)                  # :354
+    else:
+        invLy = _solve_tri(L, y, lower=True)
+        alpha = _solve_tri(L.T, invLy, lower=False)
+    return 0.5 * np.dot(y.T, alpha) + 0.5 * logK             # :355
+
+
+def calc_NLL_grad_fd(hyper_a, X, y, rel=1e-6):
+    """Central differences of ``calc_NLL`` -- the oracle for the analytic
+    gradient the GPU engine adds (the reference has none: SLSQP uses forward
+    differences, ``optimize.py:466-467``)."""
+    hyper_a = np.asarray(hyper_a, dtype=np.float64)
+    g = np.zeros_like(hyper_a)
+    for j in range(hyper_a.size):
+        h = rel * max(1.0, abs(hyper_a[j]))
+        hp = hyper_a.copy(); hp[j] += h
+        hm = hyper_a.copy(); hm[j] -= h
+        g[j] = (calc_NLL(hp, X, y, False) - calc_NLL(hm, X, y, False)) / (2 * h)
+    return g
+
+
+def calc_NLL_grad_analytic(hyper_a, X, y):
+    """Closed-form gradient (Rasmussen & Williams eq. 5.9) in the reference's
+    parametrisation hyper=[ell.., sf, sn] (standard deviations, not logs,
+    ``gp_class.py:139-142``).  d/dtheta = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta).
+    CPU cross-check of the GPU gradient kernel; validated against
+    ``calc_NLL_grad_fd`` in tests."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    hyper_a = np.asarray(hyper_a, dtype=np.float64)
+    n, D = X.shape
+    ell = hyper_a[:D]; sf = hyper_a[D]; sn = hyper_a[D + 1]
+    Kf = covSEard(X, X, ell, sf ** 2)
+    K = Kf + sn ** 2 * np.eye(n)
+    L = np.linalg.cholesky(K)
+    Linv = _solve_tri(L, np.eye(n), lower=True)
+    Kinv = Linv.T @ Linv
+    alpha = Kinv @ y
+    W = Kinv - np.outer(alpha, alpha)
+    g = np.zeros(D + 2)
+    for d in range(D):
+        diff2 = (X[:, d][:, None] - X[:, d][None, :]) ** 2
+        g[d] = 0.5 * np.sum(W * Kf * diff2) / ell[d] ** 3
+    g[D] = 0.5 * np.sum(W * Kf) * 2.0 / sf
+    g[D + 1] = 0.5 * np.trace(W) * 2.0 * sn
+    return g
+
+
+# ----------------------------------------------------------------------------
+# a5  post-fit block: chol, invK, alpha per output
+# ----------------------------------------------------------------------------
+def postfit(X, Y, hyper, lapack_general_solve=True):
+    """``optimize.py:472-494`` (twins ``:267-285``, ``gp_class.py:516-537``).
+
+    hyper:(Ny, Nx+2[+mean params]); zero prior mean ('zero' mean function, the
+    only one the numpy path supports, ``optimize.py:377-379``).
+    Returns dict(chol:(Ny,N,N) lower with zeros above, alpha:(Ny,N),
+    invK:(Ny,N,N), jitter:(Ny,) bool).
+    """
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    hyper = np.atleast_2d(np.asarray(hyper, dtype=np.float64))
+    N = X.shape[0]
+    Ny = hyper.shape[0]
+    chol = np.zeros((Ny, N, N)); invK = np.zeros((Ny, N, N)); alpha = np.zeros((Ny, N))
+    jit = np.zeros(Ny, dtype=bool)
+    for a in range(Ny):
+        K = assemble_K(X, hyper[a])
+        L, jit[a] = chol_with_jitter(K)
+        if lapack_general_solve or _solve_tri is None:
+            invL = np.linalg.solve(L, np.eye(N))                         # :489
+            invK[a] = np.linalg.solve(L.T, invL)                         # :490
+            alpha[a] = np.linalg.solve(L.T, np.linalg.solve(L, Y[:, a]))  # :494
+        else:
+            invL = _solve_tri(L, np.eye(N), lower=True)
+            invK[a] = _solve_tri(L.T, invL, lower=False)
+            alpha[a] = _solve_tri(L.T, _solve_tri(L, Y[:, a], lower=True), lower=False)
+        chol[a] = L                                                      # :491
+    return dict(chol=chol, alpha=alpha, invK=invK, jitter=jit)
+
+
+# ----------------------------------------------------------------------------
+# a8/a9/a10  posterior mean / variance / Jacobian / Taylor covariance
+# ----------------------------------------------------------------------------
+def gp_mean_var(X, hyper, alpha, chol, Z, lapack_general_solve=False):
+    """Restatement of ``build_gp`` ``gp_functions.py:111-136`` for a batch.
+
+    per output a:  ks_i = covSE(X_i, z, ell_a, sf2_a)        (:114-117,132)
+                   mean_a = ks^T alpha_a + 0                 (:119-120,135; the
+                       prior mean is always 'zero' because GP.__init__ never
+                       forwards meanFunc, gp_class.py:69-71)
+                   v = L_a \\ ks ;  var_a = sf2_a - v^T v      (:122-126,133,136)
+    Z:(H,Nx) in the GP's (standardised) input space.  Returns mean:(H,Ny),
+    var:(H,Ny).  Noise is NOT added (q3).
+    """
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+    hyper = np.atleast_2d(np.asarray(hyper, dtype=np.float64))
+    Ny = hyper.shape[0]
+    Nx = X.shape[1]
+    H = Z.shape[0]
+    mean = np.zeros((H, Ny)); var = np.zeros((H, Ny))
+    for a in range(Ny):
+        ell = hyper[a, :Nx]; sf2 = hyper[a, Nx] ** 2
+        ks = covSEard(X, Z, ell, sf2)                       # (N,H)
+        mean[:, a] = ks.T @ alpha[a]
+        if lapack_general_solve or _solve_tri is None:
+            v = np.linalg.solve(chol[a], ks)                # GP.covar style, gp_class.py:379
+        else:
+            v = _solve_tri(chol[a], ks, lower=True)         # ca.solve on lower-sparsity L
+        var[:, a] = sf2 - np.sum(v * v, axis=0)
+    return mean, var
+
+
+def gp_mean_jac(X, hyper, alpha, Z):
+    """Closed form of ``ca.jacobian(mean_func(z), z)`` ``gp_functions.py:146-147``:
+    J[a,d] = sum_i alpha_{a,i} ks_i (X_{i,d} - z_d) / ell_{a,d}^2.
+    Returns (H,Ny,Nx).  Cross-checked by central differences in tests."""
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+    hyper = np.atleast_2d(np.asarray(hyper, dtype=np.float64))
+    Ny = hyper.shape[0]; Nx = X.shape[1]; H = Z.shape[0]
+    J = np.zeros((H, Ny, Nx))
+    for a in range(Ny):
+        ell = hyper[a, :Nx]; sf2 = hyper[a, Nx] ** 2
+        ks = covSEard(X, Z, ell, sf2)                       # (N,H)
+        w = ks * alpha[a][:, None]                          # (N,H)
+        for d in range(Nx):
+            diff = X[:, d][:, None] - Z[:, d][None, :]      # (N,H)
+            J[:, a, d] = np.sum(w * diff, axis=0) / ell[d] ** 2
+    return J
+
+
+def ta_cov(var, J, Sigma):
+    """``build_TA_cov`` ``gp_functions.py:167-171``: diag(var) + J Sigma J^T.
+    var:(H,Ny) J:(H,Ny,Nx) Sigma:(Nx,Nx) or (H,Nx,Nx) -> (H,Ny,Ny)."""
+    var = np.asarray(var); J = np.asarray(J)
+    H, Ny = var.shape
+    Sigma = np.asarray(Sigma, dtype=np.float64)
+    if Sigma.ndim == 2:
+        Sigma = np.broadcast_to(Sigma, (H,) + Sigma.shape)
+    cov = np.zeros((H, Ny, Ny))
+    for h in range(H):
+        cov[h] = np.diag(var[h]) + J[h] @ Sigma[h] @ J[h].T
+    return cov
+
+
+def me_cov(var):
+    """'ME' covariance ``gp_functions.py:142`` / ``gp_class.py:213-215``: diag(var)."""
+    var = np.asarray(var)
+    H, Ny = var.shape
+    cov = np.zeros((H, Ny, Ny))
+    for h in range(H):
+        cov[h] = np.diag(var[h])
+    return cov
+
+
+# ----------------------------------------------------------------------------
+# 'EM' exact moment matching  (next-row f2; restated for parity tests)
+# ----------------------------------------------------------------------------
+def _maha(a1, b1, Q1):
+    """``maha`` ``gp_functions.py:421-430``."""
+    aQ = a1 @ Q1
+    bQ = b1 @ Q1
+    return (np.sum(aQ * a1, 1)[:, None] + np.sum(bQ * b1, 1)[None, :]
+            - 2 * aQ @ b1.T)
+
+
+def gp_exact_moment(invK, X, Y, hyper, inputmean, inputcov):
+    """``gp_exact_moment`` ``gp_functions.py:344-418``, one test point.
+
+    Quirks kept: hyper=log(hyper) then exponentiated (:367); det through the
+    product of the QR diagonal (:378-380) -- restated with slogdet's value
+    (identical when the QR diagonal is positive, NaN otherwise in the
+    reference); ``A -= invK[a]`` on the diagonal blocks (:410-411); ``+sf2``
+    (:415); ``- mean mean^T`` (:416).  Returns mean:(Ny,), cov:(Ny,Ny)
+    (standardised space; zero prior mean).
+    """
+    X = np.asarray(X, dtype=np.float64); Y = np.asarray(Y, dtype=np.float64)
+    hyper = np.atleast_2d(np.asarray(hyper, dtype=np.float64))
+    inputmean = np.asarray(inputmean, dtype=np.float64).reshape(1, -1)
+    inputcov = np.asarray(inputcov, dtype=np.float64)
+    lh = np.log(hyper)
+    Ny = len(invK)
+    N, Nx = X.shape
+    mean = np.zeros(Ny); beta = np.zeros((N, Ny)); log_k = np.zeros((N, Ny))
+    v = X - np.repeat(inputmean, N, 0)
+    covariance = np.zeros((Ny, Ny))
+    det = np.linalg.det
+    eye = np.eye(Nx)
+    for a in range(Ny):
+        beta[:, a] = invK[a] @ Y[:, a]
+        iLambda = np.diag(np.exp(-2 * lh[a, :Nx]))
+        R = inputcov + np.diag(np.exp(2 * lh[a, :Nx]))
+        iR = iLambda @ (eye - np.linalg.solve(eye + inputcov @ iLambda, inputcov @ iLambda))
+        T = v @ iR
+        c = np.exp(2 * lh[a, Nx]) / np.sqrt(det(R)) * np.exp(np.sum(lh[a, :Nx]))
+        q2 = c * np.exp(-np.sum(T * v, 1) * 0.5)
+        qb = q2 * beta[:, a]
+        mean[a] = np.sum(qb)
+        t = np.repeat(np.exp(lh[a, :Nx]).reshape(1, -1), N, 0)
+        v1 = v / t
+        log_k[:, a] = 2 * lh[a, Nx] - np.sum(v1 * v1, 1) * 0.5
+    for a in range(Ny):
+        ii = v / np.exp(2 * lh[a, :Nx])[None, :]
+        for b in range(a + 1):
+            R = inputcov @ np.diag(np.exp(-2 * lh[a, :Nx]) + np.exp(-2 * lh[b, :Nx])) + eye
+            t = 1.0 / np.sqrt(det(R))
+            ij = v / np.exp(2 * lh[b, :Nx])[None, :]
+            Q = np.exp(log_k[:, a][:, None] + log_k[:, b][None, :]
+                       + _maha(ii, -ij, np.linalg.solve(R, inputcov * 0.5)))
+            A = np.outer(beta[:, a], beta[:, b])
+            if b == a:
+                A = A - invK[a]
+            A = A * Q
+            covariance[a, b] = t * np.sum(A)
+            covariance[b, a] = covariance[a, b]
+        covariance[a, a] = covariance[a, a] + np.exp(2 * lh[a, Nx])
+    covariance = covariance - np.outer(mean, mean)
+    return mean, covariance
+
+
+# ----------------------------------------------------------------------------
+# a11/a12/a13  predict wrapper, linearisation, scalers
+# ----------------------------------------------------------------------------
+def standardize(v, mean, std):
+    """``gp_class.py:629-630`` / ``optimize.py:580-582``."""
+    return (v - mean) / std
+
+
+def inverse_mean(x, mean, std):
+    """``gp_class.py:635-638``."""
+    return (x * std) + mean
+
+
+def data_stats(X, Y, Ny):
+    """``GP.optimize`` ``gp_class.py:92-99`` (population std, ddof=0)."""
+    X = np.asarray(X, dtype=np.float64); Y = np.asarray(Y, dtype=np.float64)
+    return dict(meanY=np.mean(Y, 0), stdY=np.std(Y, 0),
+                meanZ=np.mean(X, 0), stdZ=np.std(X, 0),
+                meanX=np.mean(X[:, :Ny], 0), stdX=np.std(X[:, :Ny], 0),
+                meanU=np.mean(X[:, Ny:], 0), stdU=np.std(X[:, Ny:], 0))
+
+
+def predict(model, x, u, cov, method='TA'):
+    """``GP.predict`` ``gp_class.py:245-263`` + ``set_method`` ``:212-224``.
+
+    ``model`` = dict(X, Y, hyper, alpha, chol, invK, normalize, meta).
+    Standardises x,u when normalize (:253-255); the input covariance is used
+    as-is and the output covariance is NOT rescaled (:259-262, q4); the mean is
+    de-standardised (:260).  Returns mean:(Ny,1), cov:(Ny,Ny) like the DMs the
+    reference returns.
+    """
+    X = model['X']; hyper = model['hyper']
+    Ny = np.atleast_2d(hyper).shape[0]
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    u = np.asarray(u, dtype=np.float64).reshape(-1)
+    if model.get('normalize', False):
+        m = model['meta']
+        x_s = standardize(x, np.asarray(m['meanX']), np.asarray(m['stdX']))
+        u_s = standardize(u, np.asarray(m['meanU']), np.asarray(m['stdU']))
+    else:
+        x_s, u_s = x, u
+    z = np.concatenate([x_s, u_s]).reshape(1, -1)
+    if method == 'ME':
+        mean, var = gp_mean_var(X, hyper, model['alpha'], model['chol'], z)
+        c = me_cov(var)[0]; mu = mean[0]
+    elif method == 'TA':
+        mean, var = gp_mean_var(X, hyper, model['alpha'], model['chol'], z)
+        J = gp_mean_jac(X, hyper, model['alpha'], z)
+        c = ta_cov(var, J, np.asarray(cov, dtype=np.float64))[0]; mu = mean[0]
+    elif method == 'EM':
+        mu, c = gp_exact_moment(model['invK'], X, model['Y'], hyper, z, cov)
+    else:
+        raise NameError('No GP method called: ' + method)      # gp_class.py:237
+    if model.get('normalize', False):
+        mu = inverse_mean(mu, np.asarray(model['meta']['meanY']), np.asarray(model['meta']['stdY']))
+    return mu.reshape(Ny, 1), c
+
+
+def discrete_linearize(model, x0, u0, cov0=None):
+    """``GP.discrete_linearize`` ``gp_class.py:647-661`` for methods ME/TA:
+    A = d mean / d x, B = d mean / d u of the (standardised-space) predictor
+    (``:239-242``); inputs standardised when normalize (:656-658), outputs not
+    rescaled."""
+    hyper = model['hyper']
+    Ny = np.atleast_2d(hyper).shape[0]
+    x0 = np.asarray(x0, dtype=np.float64).reshape(-1)
+    u0 = np.asarray(u0, dtype=np.float64).reshape(-1)
+    if model.get('normalize', False):
+        m = model['meta']
+        x0 = standardize(x0, np.asarray(m['meanX']), np.asarray(m['stdX']))
+        u0 = standardize(u0, np.asarray(m['meanU']), np.asarray(m['stdU']))
+    z = np.concatenate([x0, u0]).reshape(1, -1)
+    J = gp_mean_jac(model['X'], hyper, model['alpha'], z)[0]
+    return J[:, :Ny].copy(), J[:, Ny:].copy()
+
+
+def covar(model, X_new):
+    """``GP.covar`` ``gp_class.py:353-381``: per output full posterior
+    covariance ``kss - v^T v`` between the rows of X_new, in the oddly shaped
+    (D,n,n) buffer of which only the first Ny slabs are filled (q12)."""
+    X_new = np.atleast_2d(np.asarray(X_new, dtype=np.float64))
+    n, D = X_new.shape
+    hyper = np.atleast_2d(model['hyper'])
+    Ny = hyper.shape[0]; Nx = model['X'].shape[1]
+    out = np.zeros((D, n, n))
+    for a in range(Ny):
+        ell = hyper[a, :Nx]; sf2 = hyper[a, Nx] ** 2
+        ks = covSEard_expanded(model['X'], X_new, ell, sf2)
+        v = np.linalg.solve(model['chol'][a], ks)
+        out[a] = sf2 - v.T @ v
+    return out
+
+
+def validate(model, X_test, Y_test):
+    """``GP.validate`` ``gp_class.py:145-190``: SMSE = MSE/std(Y_test) (q15),
+    MNLP with var + sn2 (:161).  Returns (SMSE, MNLP), each (Ny,)."""
+    X_test = np.asarray(X_test, dtype=np.float64).copy()
+    Y_test = np.asarray(Y_test, dtype=np.float64).copy()
+    hyper = np.atleast_2d(model['hyper'])
+    Nx = model['X'].shape[1]
+    if model.get('normalize', False):
+        m = model['meta']
+        Y_test = standardize(Y_test, np.asarray(m['meanY']), np.asarray(m['stdY']))
+        X_test = standardize(X_test, np.asarray(m['meanZ']), np.asarray(m['stdZ']))
+    N = Y_test.shape[0]
+    mean, var = gp_mean_var(model['X'], hyper, model['alpha'], model['chol'], X_test)
+    var = var + (hyper[:, Nx + 1] ** 2)[None, :]
+    loss = np.sum((Y_test - mean) ** 2, 0) / N
+    NLP = np.sum(0.5 * np.log(2 * np.pi * var) + (Y_test - mean) ** 2 / (2 * var), 0)
+    SMSE = loss / np.std(Y_test, 0)
+    MNLP = NLP / N
+    return SMSE.flatten(), MNLP.flatten()
+
+
+# ----------------------------------------------------------------------------
+# a7  hyper-parameter fit driver (SLSQP, finite differences)
+# ----------------------------------------------------------------------------
+def train_bounds_init(X, y):
+    """Bounds and initial point of ``train_gp_numpy`` ``optimize.py:433-451``
+    (zero mean).  NB ``lb[:Nx] = 1-2`` = -1 is the reference's typo (q7)."""
+    X = np.asarray(X, dtype=np.float64)
+    N, Nx = X.shape
+    num_hyp = Nx + 2
+    lb = -np.inf * np.ones(num_hyp); ub = np.inf * np.ones(num_hyp)
+    lb[:Nx] = 1 - 2
+    ub[:Nx] = 2e2
+    lb[Nx] = 1e-8
+    ub[Nx] = 1e2
+    lb[Nx + 1] = 10 ** -10
+    ub[Nx + 1] = 10 ** -2
+    bounds = np.hstack((lb.reshape(num_hyp, 1), ub.reshape(num_hyp, 1)))
+    hyp_init = np.zeros(num_hyp)
+    hyp_init[:Nx] = np.std(X, 0)
+    hyp_init[Nx] = np.std(y)
+    hyp_init[Nx + 1] = 1e-5
+    return bounds, hyp_init
+
+
+def train_gp(X, Y, options=None):
+    """``train_gp_numpy`` ``optimize.py:359-503`` restated for meanFunc='zero':
+    per output SLSQP (tol 1e-12, maxiter 1e4, finite-difference gradients,
+    ``:466-467``) from the reference's init, then the post-fit block."""
+    from scipy.optimize import minimize
+    X = np.asarray(X, dtype=np.float64); Y = np.asarray(Y, dtype=np.float64)
+    N, Nx = X.shape; Ny = Y.shape[1]
+    opts = {'disp': False, 'maxiter': 10000}
+    if options:
+        opts.update(options)
+    hyp_opt = np.zeros((Ny, Nx + 2))
+    for a in range(Ny):
+        bounds, init = train_bounds_init(X, Y[:, a])
+        res = minimize(calc_NLL, init, args=(X, Y[:, a]), method='SLSQP',
+                       options=opts, bounds=bounds, tol=1e-12)
+        hyp_opt[a] = res.x
+    out = postfit(X, Y, hyp_opt)
+    out['hyper'] = hyp_opt
+    return out
+
+
+# ----------------------------------------------------------------------------
+# fixtures / synthetic workloads shared by tests and bench
+# ----------------------------------------------------------------------------
+def synthetic_problem(N, Nx, Ny, config_id=0, H=30):
+    """Seeded synthetic workload of SURVEY.md section 8(d)."""
+    rng = np.random.default_rng(1234 + config_id)
+    X = rng.standard_normal((N, Nx))
+    W = rng.standard_normal((Nx, Ny)) / np.sqrt(Nx)
+    F = np.sin(X @ W) + 0.1 * (X @ W) ** 2
+    Y = F + 1e-2 * rng.standard_normal((N, Ny))
+    Y = (Y - Y.mean(0)) / Y.std(0)
+    hyper = np.zeros((Ny, Nx + 2))
+    hyper[:, :Nx] = rng.uniform(2.0, 6.0, size=(Ny, Nx))
+    hyper[:, Nx] = 1.0
+    hyper[:, Nx + 1] = 1e-2
+    rt = np.random.default_rng(7)
+    Z = 0.5 * rt.standard_normal((H, Nx))
+    A = rt.standard_normal((Nx, Nx))
+    Sigma = 1e-4 * np.eye(Nx) + 1e-5 * A @ A.T
+    return dict(X=X, Y=Y, hyper=hyper, Z=Z, Sigma=Sigma)
