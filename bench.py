@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- GP predictions/sec (N train x horizon test, fp64) on B200s.
+
+One "step" = one pass of the hot path over one horizon batch: H test points evaluated
+for ALL Ny outputs (mean, variance, Jacobian, first-order Taylor covariance, method
+'TA'), model resident on the device(s).  Default workload = BASELINE.json's 1/2/4/8-GPU
+configuration C5 (N=16384, Nx=10, Ny=8, H=50): the Ny independent GPs are sharded over
+the ranks (all 8 on one GPU at --gpus 1, one per GPU at --gpus 8: strong scaling), one
+NCCL all-gather of H*(2+Nx) doubles per output reassembles state/covariance.
+
+  python bench.py [--gpus N --steps K --warmup W] [--workload c5|c3|c2] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events on the
+engine's stream, max over ranks); `e2e` = the same metric through the host C-ABI call
+(host buffers, H2D/D2H inside); `roofline` = the dominant kernel (the v = L^-1 ks
+tensor-core product) against the measured fp64 GEMM peak; `cpu_baseline` = the oracle
+port of the reference's predict path on the box's host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    'c5': dict(N=16384, Nx=10, Ny=8, H=50, cfg=5, name='C5: N=16384 Nx=10 Ny=8 H=50 TA, outputs sharded over GPUs'),
+    'c3': dict(N=4096, Nx=8, Ny=6, H=30, cfg=3, name='C3: N=4096 Nx=8 Ny=6 H=30 TA'),
+    'c2': dict(N=1000, Nx=8, Ny=6, H=30, cfg=2, name='C2: N=1000 Nx=8 Ny=6 H=30 TA'),
+}
+METRIC = 'GP predictions/sec (N train x horizon test, fp64)'
+
+
+def make_workload(N, Nx, Ny, cfg, H):
+    """Seeded synthetic inputs of SURVEY.md 8(d) (same generator as the oracle's
+    synthetic_problem; tests assert they agree)."""
+    rng = np.random.default_rng(1234 + cfg)
+    X = rng.standard_normal((N, Nx))
+    W = rng.standard_normal((Nx, Ny)) / np.sqrt(Nx)
+    F = np.sin(X @ W) + 0.1 * (X @ W) ** 2
+    Y = F + 1e-2 * rng.standard_normal((N, Ny))
+    Y = (Y - Y.mean(0)) / Y.std(0)
+    hyper = np.zeros((Ny, Nx + 2))
+    hyper[:, :Nx] = rng.uniform(2.0, 6.0, size=(Ny, Nx))
+    hyper[:, Nx] = 1.0
+    hyper[:, Nx + 1] = 1e-2
+    rt = np.random.default_rng(7)
+    Z = 0.5 * rt.standard_normal((H, Nx))
+    A = rt.standard_normal((Nx, Nx))
+    Sigma = 1e-4 * np.eye(Nx) + 1e-5 * A @ A.T
+    return dict(X=X, Y=Y, hyper=hyper, Z=Z, Sigma=Sigma)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(',') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].strip().lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_predict_port(orc, X, hyper_a, alpha_a, L_a, Z):
+    """The reference's numeric predict for ONE output on the CPU (oracle port of
+    gp_functions.py:111-147 / GP.covar gp_class.py:353-381): ks, mean, v = L\\ks (true
+    triangular solve -- cheaper than the reference's LU np.linalg.solve, so conservative),
+    var, Jacobian."""
+    from scipy.linalg import solve_triangular
+    Nx = X.shape[1]
+    ell = hyper_a[:Nx]; sf2 = hyper_a[Nx] ** 2
+    ks = orc.covSEard(X, Z, ell, sf2)
+    mean = ks.T @ alpha_a
+    v = solve_triangular(L_a, ks, lower=True, check_finite=False)
+    var = sf2 - np.sum(v * v, 0)
+    w = ks * alpha_a[:, None]
+    J = np.stack([(w * (X[:, d][:, None] - Z[:, d][None, :])).sum(0) / ell[d] ** 2 for d in range(Nx)], 1)
+    return mean, var, J
+
+
+def run_reference(args, wl, rank):
+    """--impl reference: the reference's own CPU path for this metric (oracle port; the
+    reference is pure Python on numpy/CasADi, CasADi is not installable here), all host
+    threads, bounded sample: ONE of the Ny outputs factorised and predicted on the CPU, the
+    other outputs cost the same, so predictions/s = H / (Ny * t_one_output)."""
+    if rank != 0:
+        return
+    from oracle import gp_oracle as orc
+    N, Nx, Ny, H = wl['N'], wl['Nx'], wl['Ny'], wl['H']
+    Ns = N if N <= 8192 else 8192       # bounded: CPU potrf at 16384 alone is ~1 min on few cores
+    w = make_workload(Ns, Nx, Ny, wl['cfg'], H)
+    t0 = time.perf_counter()
+    K = orc.covSEard_blas(w['X'], w['X'], w['hyper'][0, :Nx], w['hyper'][0, Nx] ** 2)
+    K[np.diag_indices(Ns)] += w['hyper'][0, Nx + 1] ** 2
+    L = np.linalg.cholesky(K)
+    from scipy.linalg import solve_triangular
+    alpha = solve_triangular(L.T, solve_triangular(L, w['Y'][:, 0], lower=True), lower=False)
+    t_setup = time.perf_counter() - t0
+    for _ in range(args.warmup):
+        cpu_predict_port(orc, w['X'], w['hyper'][0], alpha, L, w['Z'])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_predict_port(orc, w['X'], w['hyper'][0], alpha, L, w['Z'])
+    dt = (time.perf_counter() - t0) / args.steps
+    scale = (N / Ns) ** 2                # predict cost is O(N^2) per test point (triangular solve)
+    t_step = dt * Ny * scale
+    val = H / t_step
+    sample = ('1 of %d outputs, N=%d%s, H=%d; per-step time x Ny%s; CPU setup (K+potrf) %.1fs not timed'
+              % (Ny, Ns, '' if Ns == N else ' (of %d)' % N, H, '' if Ns == N else ' x (N/Ns)^2', t_setup))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'predictions/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_step * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': wl['name']},
+            'cpu_baseline': {'value': val, 'unit': 'predictions/s', 'cores': os.cpu_count(), 'kind': 'port',
+                             'sample': sample},
+            'e2e': {'value': val, 'unit': 'predictions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c5', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gp_mpc_b200
+    from gp_mpc_b200 import _lib as L
+    from gp_mpc_b200.partition import output_block
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the engine has no CPU path')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    N, Nx, Ny, H = wl['N'], wl['Nx'], wl['Ny'], wl['H']
+    w = make_workload(N, Nx, Ny, wl['cfg'], H)
+
+    # ---- model set-up (not timed): data -> K -> Cholesky -> L^-1 -> alpha on the GPU ----
+    b, n = output_block(Ny, rank, world)
+    if n == 0:
+        raise SystemExit('workload %s has fewer outputs than ranks' % args.workload)
+    t0 = time.perf_counter()
+    eng = gp_mpc_b200.Engine(N, Nx, Ny, b, n, device=local_rank)
+    eng.set_data(w['X'], w['Y'])
+    eng.set_hyper(w['hyper'])
+    if world > 1:
+        box = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], rank, world)
+    eng.factorize()
+    t_setup = time.perf_counter() - t0
+
+    st = torch.cuda.ExternalStream(eng.stream())
+    dZ = torch.from_numpy(w['Z']).cuda(); dS = torch.from_numpy(w['Sigma']).cuda()
+    d_mean = torch.empty(H, Ny, dtype=torch.float64, device='cuda')
+    d_var = torch.empty_like(d_mean)
+    d_cov = torch.empty(H, Ny, Ny, dtype=torch.float64, device='cuda')
+    d_jac = torch.empty(H, Ny, Nx, dtype=torch.float64, device='cuda')
+    torch.cuda.synchronize()
+
+    def step_dev():
+        eng.predict_device(L.METHOD_TA, H, dZ.data_ptr(), dS.data_ptr(), 0, d_mean.data_ptr(), d_var.data_ptr(),
+                           d_cov.data_ptr(), d_jac.data_ptr(), sync=False)
+
+    # model bytes touched per step on this rank: L^-1 lower triangles; larger than L2 => no flush
+    model_bytes = n * 4 * N * N
+    flush = model_bytes < 4 * 126e6
+    fl = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device='cuda') if flush else None   # 256 MB
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    eng.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with torch.cuda.stream(st):
+        for e0, e1 in evs:
+            if flush:
+                fl.zero_()
+            e0.record(st)
+            step_dev()
+            e1.record(st)
+    eng.synchronize()
+    barrier()
+    ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    clocks = sampler.stop()
+    tm = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_step = float(tm.item()) / args.steps
+    value = H / (ms_step * 1e-3)
+
+    # ---- e2e through the host C-ABI call (host buffers, H2D + D2H inside the timed region) ----
+    for _ in range(2):
+        eng.predict(w['Z'], w['Sigma'], L.METHOD_TA)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mean, var, cov, jac = eng.predict(w['Z'], w['Sigma'], L.METHOD_TA)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = H * args.steps / float(te.item())
+    h2d = (H * Nx + Nx * Nx) * 8
+    d2h = (2 * H * Ny + H * Ny * Nx + H * Ny * Ny) * 8
+
+    # ---- roofline of the dominant kernel: v = L^-1 ks on the fp64 tensor pipe -----------------
+    # algorithmic work per launch: flops = n_local * H * N^2, bytes = n_local * 4 N^2
+    ms_tri = eng.profile(L.PROF_TRIGEMM, n=H, reps=max(5, args.steps))
+    flops = n * H * float(N) * N
+    achieved = flops / (ms_tri * 1e-3) / 1e12
+    # fp64 tensor peak is not in MEASURED_PEAKS.json (bf16 only): measure cuBLAS DGEMM here
+    a = torch.randn(8192, 8192, dtype=torch.float64, device='cuda'); bmat = torch.randn_like(a)
+    best = 1e9
+    for _ in range(4):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, bmat); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    dgemm_tf = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+    del a, bmat
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_dmma_kernel<BM,128,1,8,NT> (v = Linv ks, split-K)',
+                'achieved': achieved, 'peak': dgemm_tf, 'unit': 'TFLOP/s', 'frac': achieved / dgemm_tf,
+                'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (fp64 is absent from MEASURED_PEAKS.json)',
+                'ms_per_launch': ms_tri, 'traffic': None,
+                'hbm_view': {'algorithmic_gbs': n * 4.0 * N * N / (ms_tri * 1e-3) / 1e9, 'peak_gbs': hbm_peak,
+                             'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ---------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import gp_oracle as orc
+        t0 = time.perf_counter()
+        La = eng.get(L.GET_CHOL, b)           # factor computed on the GPU: the CPU leg times predict only
+        al = eng.get(L.GET_ALPHA, b)
+        reps = 0; tt = 0.0
+        while tt < 10.0 and reps < 5:
+            t1 = time.perf_counter()
+            cm, cv, cj = cpu_predict_port(orc, w['X'], w['hyper'][b], al, La, w['Z'])
+            tt += time.perf_counter() - t1; reps += 1
+        t_one = tt / reps
+        cpu = {'value': H / (t_one * Ny), 'unit': 'predictions/s', 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': 'oracle port of the numeric predict (ks, mean, L\\ks triangular solve, var, Jacobian) for 1 of '
+                         '%d outputs at full N=%d, H=%d, %d reps, time x Ny; factor taken from the GPU' % (Ny, N, H, reps),
+               'parity_vs_gpu': {'mean': float(np.abs(cm - mean[:, b]).max() / np.abs(cm).max()),
+                                 'var': float(np.abs(cv - var[:, b]).max() / np.abs(cv).max())}}
+        del La
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': 'predictions/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': wl['name'], 'method': 'TA', 'N': N, 'Nx': Nx, 'Ny': Ny, 'H': H,
+                           'parallelism': 'outputs sharded %d/GPU, NCCL all-gather' % n,
+                           'l2': 'flush 256MB between steps' if flush else 'model %.1f GB/rank > L2, no flush' % (model_bytes / 1e9),
+                           'setup_s': t_setup},
+                'clocks': clocks,
+                'e2e': {'value': e2e_val, 'unit': 'predictions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+                'gpu_launches': args.steps * (4 * ((H + 63) // 64) + 1),
+                'roofline': roofline, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,215 @@
+"""ctypes binding of libgpmpc.so (the C ABI in include/gpmpc.h).
+
+There is deliberately NO fallback: if the CUDA library has not been built
+(``python -c "import __graft_entry__ as g; g.build()"``) importing the engine
+fails loudly, and ``gpmpc_create`` fails when no sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get('GPMPC_LIB', os.path.join(_HERE, 'lib', 'libgpmpc.so'))
+
+OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NCCL, ERR_NOTPD = 0, -1, -2, -3, -4, -5
+METHOD_ME, METHOD_TA = 0, 1
+GET_CHOL, GET_ALPHA, GET_INVK, GET_K, GET_LOGDET, GET_LINV = range(6)
+PROF_KBUILD_FULL, PROF_KBUILD_LOWER, PROF_SYRK, PROF_FACTORIZE, PROF_TRIGEMM = range(5)
+
+# every symbol include/gpmpc.h declares: (name, restype, argtypes)
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_H = C.c_void_p
+SYMBOLS = [
+    ('gpmpc_version', C.c_int, []),
+    ('gpmpc_create', C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
+    ('gpmpc_destroy', C.c_int, [_H]),
+    ('gpmpc_last_error', C.c_char_p, [_H]),
+    ('gpmpc_set_data', C.c_int, [_H, _dp, _dp]),
+    ('gpmpc_set_hyper', C.c_int, [_H, _dp, C.c_int]),
+    ('gpmpc_build_K', C.c_int, [_H, C.c_int, _dp]),
+    ('gpmpc_factorize', C.c_int, [_H, C.c_double, _ip]),
+    ('gpmpc_nlml', C.c_int, [_H, C.c_int, _dp, _dp, _dp]),
+    ('gpmpc_predict', C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]),
+    ('gpmpc_predict_device', C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    ('gpmpc_get', C.c_int, [_H, C.c_int, C.c_int, _dp]),
+    ('gpmpc_set_option', C.c_int, [_H, C.c_char_p, C.c_double]),
+    ('gpmpc_comm_unique_id', C.c_int, [C.c_void_p]),
+    ('gpmpc_comm_init', C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
+    ('gpmpc_stream', C.c_void_p, [_H]),
+    ('gpmpc_synchronize', C.c_int, [_H]),
+    ('gpmpc_profile', C.c_int, [_H, C.c_int, C.c_int, C.c_int, _dp]),
+]
+
+_lib = None
+
+
+class GpmpcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('gpmpc error %d: %s' % (code, msg))
+        self.code = code
+
+
+def load():
+    """Load libgpmpc.so once; raises ImportError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'libgpmpc.so not found at %s -- build it with `python -c "import __graft_entry__ as g; '
+            'g.build()"` (nvcc, sm_100a).  This engine has no CPU fallback.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)      # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Engine:
+    """One handle = one GPU.  Thin, typed veneer over the C ABI; all heavy work is CUDA."""
+
+    def __init__(self, N, Nx, Ny, out_begin=0, out_count=None, device=0):
+        self.lib = load()
+        self.N, self.Nx, self.Ny = int(N), int(Nx), int(Ny)
+        self.out_begin = int(out_begin)
+        self.out_count = int(Ny - out_begin if out_count is None else out_count)
+        self.device = int(device)
+        self.h = _H()
+        rc = self.lib.gpmpc_create(self.N, self.Nx, self.Ny, self.out_begin, self.out_count, self.device,
+                                   C.byref(self.h))
+        if rc != OK:
+            msg = self.lib.gpmpc_last_error(None).decode()
+            self.h = None
+            raise GpmpcError(rc, msg)
+
+    # -- plumbing ---------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != OK:
+            raise GpmpcError(rc, self.lib.gpmpc_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.gpmpc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def local_outputs(self):
+        return range(self.out_begin, self.out_begin + self.out_count)
+
+    # -- model ------------------------------------------------------------------------
+    def set_data(self, X, Y):
+        X = _f64(X, (self.N, self.Nx)); Y = _f64(Y, (self.N, self.Ny))
+        self._check(self.lib.gpmpc_set_data(self.h, _ptr(X), _ptr(Y)))
+
+    def set_hyper(self, hyper):
+        hyper = _f64(hyper)
+        assert hyper.ndim == 2 and hyper.shape[0] == self.Ny and hyper.shape[1] >= self.Nx + 2
+        self._check(self.lib.gpmpc_set_hyper(self.h, _ptr(hyper), hyper.shape[1]))
+
+    def build_K(self, a):
+        K = np.empty((self.N, self.N))
+        self._check(self.lib.gpmpc_build_K(self.h, int(a), _ptr(K)))
+        return K
+
+    def factorize(self, jitter=1e-8):
+        info = np.zeros(self.out_count, dtype=np.int32)
+        rc = self.lib.gpmpc_factorize(self.h, float(jitter), info.ctypes.data_as(_ip))
+        if rc == ERR_NOTPD:
+            raise np.linalg.LinAlgError(self.lib.gpmpc_last_error(self.h).decode())
+        self._check(rc)
+        return info
+
+    def nlml(self, a, theta, grad=True):
+        theta = _f64(theta, (self.Nx + 2,))
+        nll = C.c_double(0.0)
+        g = np.empty(self.Nx + 2) if grad else None
+        rc = self.lib.gpmpc_nlml(self.h, int(a), _ptr(theta), C.byref(nll), _ptr(g))
+        if rc == ERR_NOTPD:
+            raise np.linalg.LinAlgError(self.lib.gpmpc_last_error(self.h).decode())
+        self._check(rc)
+        return (nll.value, g) if grad else nll.value
+
+    def get(self, what, a):
+        N = self.N
+        shape = {GET_CHOL: (N, N), GET_LINV: (N, N), GET_INVK: (N, N), GET_K: (N, N),
+                 GET_ALPHA: (N,), GET_LOGDET: (1,)}[what]
+        out = np.empty(shape)
+        self._check(self.lib.gpmpc_get(self.h, int(what), int(a), _ptr(out)))
+        return out
+
+    def set_option(self, name, value):
+        self._check(self.lib.gpmpc_set_option(self.h, name.encode(), float(value)))
+
+    # -- predict ----------------------------------------------------------------------
+    def predict(self, Z, Sigma=None, method=METHOD_TA, want_cov=True, want_jac=True):
+        """Z:(H,Nx) -> mean:(H,Ny), var:(H,Ny), cov:(H,Ny,Ny)|None, jac:(H,Ny,Nx)|None (host arrays)."""
+        Z = _f64(Z).reshape(-1, self.Nx)
+        H = Z.shape[0]
+        spp = 0
+        if Sigma is not None:
+            Sigma = _f64(Sigma)
+            if Sigma.ndim == 3:
+                assert Sigma.shape == (H, self.Nx, self.Nx)
+                spp = 1
+            else:
+                assert Sigma.shape == (self.Nx, self.Nx)
+        mean = np.empty((H, self.Ny)); var = np.empty((H, self.Ny))
+        cov = np.empty((H, self.Ny, self.Ny)) if want_cov else None
+        jac = np.empty((H, self.Ny, self.Nx)) if want_jac else None
+        self._check(self.lib.gpmpc_predict(self.h, int(method), H, _ptr(Z), _ptr(Sigma), spp,
+                                           _ptr(mean), _ptr(var), _ptr(cov), _ptr(jac)))
+        return mean, var, cov, jac
+
+    def predict_device(self, method, H, dZ, dSigma, spp, d_mean, d_var, d_cov, d_jac, sync=False):
+        """Raw device-pointer variant (ints); enqueues on the handle's stream."""
+        self._check(self.lib.gpmpc_predict_device(self.h, int(method), int(H), dZ, dSigma, int(spp),
+                                                  d_mean, d_var, d_cov, d_jac, 1 if sync else 0))
+
+    # -- multi-GPU --------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        lib = load()
+        buf = C.create_string_buffer(128)
+        rc = lib.gpmpc_comm_unique_id(buf)
+        if rc != OK:
+            raise GpmpcError(rc, lib.gpmpc_last_error(None).decode())
+        return bytes(buf.raw)
+
+    def comm_init(self, uid, rank, world):
+        buf = C.create_string_buffer(bytes(uid), 128)
+        self._check(self.lib.gpmpc_comm_init(self.h, buf, int(rank), int(world)))
+
+    def stream(self):
+        return self.lib.gpmpc_stream(self.h)
+
+    def synchronize(self):
+        self._check(self.lib.gpmpc_synchronize(self.h))
+
+    def profile(self, what, n=0, reps=5):
+        ms = C.c_double(0.0)
+        self._check(self.lib.gpmpc_profile(self.h, int(what), int(n), int(reps), C.byref(ms)))
+        return ms.value

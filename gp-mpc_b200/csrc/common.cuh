@@ -1,0 +1,49 @@
+// Shared helpers for the gpmpc CUDA translation unit (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define GPMPC_TILE 128          // all internal matrices are padded to a multiple of this
+
+#define CUDA_TRY(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) {                                              \
+            set_error(h, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,         \
+                      cudaGetErrorString(_e));                                \
+            return GPMPC_ERR_CUDA;                                            \
+        }                                                                     \
+    } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 16-byte asynchronous global->shared copy (LDGSTS), L2-only caching: tiles are
+// streamed once per CTA, reuse happens in L2 across CTAs.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory");
+}
+
+// fp64 tensor-core MMA: D(8x8) = A(8x4,row) * B(4x8,col) + C.  SASS: DMMA.8x8x4.
+// lane l holds A[l/4][l%4], B[k=l%4][n=l/4], C/D[l/4][2*(l%4)+{0,1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile(
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

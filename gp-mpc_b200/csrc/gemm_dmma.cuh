@@ -1,0 +1,205 @@
+// fp64 tensor-core (DMMA m8n8k4) GEMM family used by every O(N^3) / O(N^2 H) step of the
+// GP hot path: Cholesky trailing updates (SYRK), explicit-inverse panel solves, the
+// triangular inverse assembly, K^-1 = Linv^T Linv, and the batched predictive
+// v = Linv * ks product.  Blackwell has no fp64 tcgen05 kind, so the fp64 tensor path
+// is mma.sync.m8n8k4 (SASS DMMA.8x8x4) fed by a 4-stage cp.async shared-memory pipeline.
+//
+//   C[i][j] = alpha * sum_k A[i][k] * Bop[k][j] + beta * Cin[i][j]
+//   A   : row-major M x K (K contiguous)
+//   BT  : B is row-major N x K  (C = A * B^T, "NT")
+//   !BT : B is row-major K x N  (C = A * B,   "NN")
+//
+// All dimensions are multiples of the tile sizes (every matrix in the engine is padded
+// to GPMPC_TILE with an identity tail), so there is no bounds handling anywhere.
+#pragma once
+#include "common.cuh"
+
+enum : int {
+    GEMM_KI_LE = 1,   // A[i][k] == 0 for k >  i  (A lower-triangular)  -> k_hi <= (it+1)*BM
+    GEMM_KI_GE = 2,   // A[i][k] == 0 for k <  i  (A upper-triangular)  -> k_lo >= it*BM
+    GEMM_KJ_LE = 4,   // Bop[k][j] == 0 for k > j                       -> k_hi <= (jt+1)*BN
+    GEMM_KJ_GE = 8,   // Bop[k][j] == 0 for k < j                       -> k_lo >= jt*BN
+};
+
+struct GemmParams {
+    const double* A; const double* B; double* C; const double* Cin;
+    int lda, ldb, ldc, ldcin;
+    long long sA, sB, sC, sCin;     // batch strides in elements (blockIdx.z)
+    int mt, nt;                      // tile counts in M and N
+    int K;
+    double alpha, beta;
+    int kflags;
+    int lower;                       // compute tiles it >= jt only; mask col > row on diagonal tiles
+    int ksplit;                      // split-K chunk length (multiple of 16), 0 = off (blockIdx.y = chunk)
+    long long sPart;                 // element stride between split-K partial outputs
+};
+
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 4;
+
+template <int BM, int BN, bool BT>
+struct GemmSmem {
+    static constexpr int LDA_S = GEMM_BK + 4;                 // 160 B rows: (g*32 + t*8) mod 128 distinct
+    static constexpr int LDB_S = BT ? (GEMM_BK + 4) : (BN + 4);
+    static constexpr int A_STAGE = BM * LDA_S;
+    static constexpr int B_STAGE = BT ? BN * LDB_S : GEMM_BK * LDB_S;
+    static constexpr int BYTES = GEMM_STAGES * (A_STAGE + B_STAGE) * 8;
+};
+
+template <int BM, int BN, int WM, int WN, bool BT>
+__global__ void __launch_bounds__(WM * WN * 32, 1)
+gemm_dmma_kernel(const GemmParams p)
+{
+    using SM = GemmSmem<BM, BN, BT>;
+    constexpr int BK = GEMM_BK, STAGES = GEMM_STAGES, NT = WM * WN * 32;
+    constexpr int LDA_S = SM::LDA_S, LDB_S = SM::LDB_S, A_STAGE = SM::A_STAGE, B_STAGE = SM::B_STAGE;
+    constexpr int WTM = BM / WM, WTN = BN / WN, MF = WTM / 8, NF = WTN / 8;
+    static_assert(WTM % 8 == 0 && WTN % 8 == 0, "warp tile must be a multiple of the 8x8 MMA");
+
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * A_STAGE;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
+
+    int it, jt;
+    if (p.lower) {
+        const int tt = blockIdx.x;
+        it = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
+        while (it * (it + 1) / 2 > tt) --it;
+        while ((it + 1) * (it + 2) / 2 <= tt) ++it;
+        jt = tt - it * (it + 1) / 2;
+    } else {
+        it = blockIdx.x / p.nt;
+        jt = blockIdx.x - it * p.nt;
+    }
+
+    int k_lo = 0, k_hi = p.K;
+    if (p.kflags & GEMM_KI_LE) k_hi = min(k_hi, (it + 1) * BM);
+    if (p.kflags & GEMM_KI_GE) k_lo = max(k_lo, it * BM);
+    if (p.kflags & GEMM_KJ_LE) k_hi = min(k_hi, (jt + 1) * BN);
+    if (p.kflags & GEMM_KJ_GE) k_lo = max(k_lo, jt * BN);
+    long long part_off = 0;
+    if (p.ksplit) {
+        const int cs = blockIdx.y * p.ksplit;
+        k_lo = max(k_lo, cs);
+        k_hi = min(k_hi, cs + p.ksplit);
+        if (k_lo >= k_hi) return;            // the reducer applies the same chunk-validity rule
+        part_off = (long long)blockIdx.y * p.sPart;
+    }
+    const int nk = (k_hi - k_lo) / BK;
+
+    const long long bz = blockIdx.z;
+    const double* Ag = p.A + bz * p.sA + (long long)it * BM * p.lda;
+    const double* Bg = BT ? (p.B + bz * p.sB + (long long)jt * BN * p.ldb)
+                          : (p.B + bz * p.sB + (long long)jt * BN);
+
+    auto load_stage = [&](int s, int k0) {
+        double* as = As + s * A_STAGE;
+        double* bs = Bs + s * B_STAGE;
+#pragma unroll
+        for (int c = tid; c < BM * 8; c += NT) {
+            const int r = c >> 3, ch = c & 7;
+            cp_async16(as + r * LDA_S + ch * 2, Ag + (long long)r * p.lda + k0 + ch * 2);
+        }
+        if (BT) {
+#pragma unroll
+            for (int c = tid; c < BN * 8; c += NT) {
+                const int r = c >> 3, ch = c & 7;
+                cp_async16(bs + r * LDB_S + ch * 2, Bg + (long long)r * p.ldb + k0 + ch * 2);
+            }
+        } else {
+#pragma unroll
+            for (int c = tid; c < BK * (BN / 2); c += NT) {
+                const int r = c / (BN / 2), ch = c % (BN / 2);
+                cp_async16(bs + r * LDB_S + ch * 2, Bg + (long long)(k0 + r) * p.ldb + ch * 2);
+            }
+        }
+    };
+
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NF; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, k_lo + s * BK);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {   // prefetch the stage that was consumed in the previous iteration
+            const int kn = kt + STAGES - 1;
+            if (kn < nk) load_stage(kn % STAGES, k_lo + kn * BK);
+            cp_async_commit();
+        }
+        const int s = kt % STAGES;
+        const double* as = As + s * A_STAGE + (wm * WTM + g) * LDA_S + t;
+        const double* bs = BT ? (Bs + s * B_STAGE + (wn * WTN + g) * LDB_S + t)
+                              : (Bs + s * B_STAGE + t * LDB_S + wn * WTN + g);
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[MF], b[NF];
+#pragma unroll
+            for (int mi = 0; mi < MF; ++mi) a[mi] = as[mi * 8 * LDA_S + kk * 4];
+#pragma unroll
+            for (int ni = 0; ni < NF; ++ni)
+                b[ni] = BT ? bs[ni * 8 * LDB_S + kk * 4] : bs[kk * 4 * LDB_S + ni * 8];
+#pragma unroll
+            for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NF; ++ni)
+                    dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: each lane owns two adjacent columns of every 8x8 fragment -> 16-byte accesses
+    double* Cg = p.C + bz * p.sC + part_off;
+    const double* Cing = p.Cin ? (p.Cin + bz * p.sCin) : nullptr;
+    const bool diag = p.lower && (it == jt);
+#pragma unroll
+    for (int mi = 0; mi < MF; ++mi) {
+        const int row = it * BM + wm * WTM + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < NF; ++ni) {
+            const int col = jt * BN + wn * WTN + ni * 8 + 2 * t;
+            double2 c;
+            c.x = p.alpha * acc[mi][ni][0];
+            c.y = p.alpha * acc[mi][ni][1];
+            if (diag && col > row) continue;
+            if (p.beta != 0.0) {
+                const double2 cin = *reinterpret_cast<const double2*>(Cing + (long long)row * p.ldcin + col);
+                c.x += p.beta * cin.x;
+                c.y += p.beta * cin.y;
+            }
+            double* dst = Cg + (long long)row * p.ldc + col;
+            if (diag && col + 1 > row) dst[0] = c.x;
+            else *reinterpret_cast<double2*>(dst) = c;
+        }
+    }
+}
+
+template <int BM, int BN, int WM, int WN, bool BT>
+static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cudaStream_t st)
+{
+    using SM = GemmSmem<BM, BN, BT>;
+    auto kern = gemm_dmma_kernel<BM, BN, WM, WN, BT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = p.lower ? p.mt * (p.mt + 1) / 2 : p.mt * p.nt;
+    dim3 grid(tiles, p.ksplit ? nchunks : 1, batch);
+    kern<<<grid, WM * WN * 32, SM::BYTES, st>>>(p);
+    return cudaGetLastError();
+}

@@ -1,0 +1,889 @@
+// libgpmpc.so -- host side of the C ABI declared in include/gpmpc.h.
+// One handle = one GPU = one CUDA stream.  No CPU fallback exists in this library.
+#include "../../include/gpmpc.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+#include "kernels.cuh"
+
+#define GPMPC_VERSION 100
+#define HB 64                 // test points per predict pass (rows of the KS^T operand)
+#define MAX_CHUNKS 16         // split-K partial slots per output
+#define NX_MAX 32
+
+// ------------------------------------------------------------------------------------
+// minimal NCCL surface, bound at run time with dlopen (no link-time dependency)
+// ------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static char g_create_err[512] = "";
+
+static bool nccl_load(char* err, size_t errn)
+{
+    if (g_nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { snprintf(err, errn, "dlopen(libnccl.so.2) failed: %s", dlerror()); return false; }
+    g_nccl.GetUniqueId = (int (*)(nccl_uid_t*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid_t, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+        snprintf(err, errn, "libnccl is missing required symbols");
+        g_nccl.lib = nullptr;
+        return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------
+struct gpmpc_handle_s {
+    int N = 0, Nx = 0, Ny = 0, a0 = 0, nloc = 0, Npad = 0, device = 0;
+    int nloc_max = 0;                 // ceil(Ny / world): slots per rank in the gather buffer
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // model
+    double *dXT = nullptr, *dY = nullptr, *dHyp = nullptr, *dJit = nullptr, *dHypTmp = nullptr;
+    double *dL = nullptr, *dLi = nullptr, *dW1 = nullptr, *dW2 = nullptr;
+    double *dAlpha = nullptr, *dTmp = nullptr, *dRes = nullptr;
+    int* dInfo = nullptr;
+    // predict
+    double *dKST = nullptr, *dPart = nullptr, *dPMJ = nullptr, *dSQ = nullptr, *dV = nullptr, *dR = nullptr;
+    double *dG = nullptr, *dZ = nullptr, *dSigma = nullptr, *dMean = nullptr, *dVar = nullptr, *dJ = nullptr, *dCov = nullptr;
+    int Hcap = 0;
+    double* hPinned = nullptr; size_t hPinnedBytes = 0;
+    // nlml scratch
+    double *dU = nullptr, *dKinv = nullptr, *dGradPart = nullptr, *dGrad = nullptr;
+    bool has_data = false, has_hyper = false, factorized = false;
+    std::vector<double> hyper;        // (nloc, Nx+2)
+    std::vector<double> logdet, yalpha;
+    std::vector<int> jitter_used;
+    int opt_refine = 0, opt_ksplit = 0;
+    // comm
+    nccl_comm_t comm = nullptr; int rank = 0, world = 1;
+    char err[512] = "";
+};
+
+static void set_error(gpmpc_handle_t h, const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(h ? h->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+}
+
+static inline long long slab(gpmpc_handle_t h) { return (long long)h->Npad * h->Npad; }
+static inline long long wslab(gpmpc_handle_t h) { return (long long)h->Npad * h->Npad / 4 + 128; }
+
+// ------------------------------------------------------------------------------------
+// GEMM helpers (all operands live in slabs with leading dimension ld)
+// ------------------------------------------------------------------------------------
+static cudaError_t gemm128(gpmpc_handle_t h, bool bt, const GemmParams& p, int batch)
+{
+    return bt ? gemm_launch<128, 128, 2, 4, true>(p, batch, 1, h->st)
+              : gemm_launch<128, 128, 2, 4, false>(p, batch, 1, h->st);
+}
+
+// Recursive blocked Cholesky + triangular inverse on the diagonal block
+// [off, off+n) of every slab in the batch:  A -> L (in place, lower), Li -> L^-1.
+//   1. (L11, Li11) = rec(A11)
+//   2. L21 = A21 Li11^T                 (explicit-inverse panel solve, DMMA GEMM NT)
+//   3. A22 -= L21 L21^T                 (trailing SYRK update, DMMA GEMM NT, lower tiles)
+//   4. (L22, Li22) = rec(A22)
+//   5. Li21 = -Li22 (L21 Li11)          (two DMMA GEMMs NN)
+// All flops except the 128x128 leaves run on the fp64 tensor pipe.
+static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, long long sLi,
+                         int* dInfo, int off, int n, int batch)
+{
+    const int ld = h->Npad;
+    if (n <= LEAF_N) {
+        static bool conf = false;
+        const int smem = LEAF_N * LEAF_LD * 8;
+        if (!conf) {
+            CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            conf = true;
+        }
+        leaf_potrf_trtri_kernel<<<batch, 256, smem, h->st>>>(A + (long long)off * ld + off, ld, sA,
+                                                              Li + (long long)off * ld + off, ld, sLi, dInfo, off);
+        CUDA_TRY(cudaGetLastError());
+        return GPMPC_OK;
+    }
+    const int nb = n / GPMPC_TILE;
+    const int n1 = (nb / 2) * GPMPC_TILE, n2 = n - n1;
+    int rc = potrf_inv_rec(h, A, Li, sA, sLi, dInfo, off, n1, batch);
+    if (rc) return rc;
+    double* A21 = A + (long long)(off + n1) * ld + off;
+    double* A22 = A + (long long)(off + n1) * ld + off + n1;
+    double* Li11 = Li + (long long)off * ld + off;
+    double* Li21 = Li + (long long)(off + n1) * ld + off;
+    double* Li22 = Li + (long long)(off + n1) * ld + off + n1;
+    const long long sW = wslab(h);
+    GemmParams p;
+    // 2. W1 = A21 * Li11^T      B[j][k] = Li11[j][k] != 0 only for k <= j
+    memset(&p, 0, sizeof(p));
+    p.A = A21; p.lda = ld; p.sA = sA;
+    p.B = Li11; p.ldb = ld; p.sB = sLi;
+    p.C = h->dW1; p.ldc = n1; p.sC = sW;
+    p.mt = n2 / 128; p.nt = n1 / 128; p.K = n1; p.alpha = 1.0; p.beta = 0.0; p.kflags = GEMM_KJ_LE;
+    CUDA_TRY(gemm128(h, true, p, batch));
+    {   // L21 <- W1
+        dim3 g(std::max(1, std::min(64, n1 / 2 / 128)), std::min(n2, 4096), batch);
+        copy2d_kernel<<<g, 128, 0, h->st>>>(h->dW1, n1, sW, A21, ld, sA, n2, n1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    // 3. A22 -= W1 * W1^T   (lower tiles only)
+    memset(&p, 0, sizeof(p));
+    p.A = h->dW1; p.lda = n1; p.sA = sW;
+    p.B = h->dW1; p.ldb = n1; p.sB = sW;
+    p.C = A22; p.ldc = ld; p.sC = sA; p.Cin = A22; p.ldcin = ld; p.sCin = sA;
+    p.mt = n2 / 128; p.nt = n2 / 128; p.K = n1; p.alpha = -1.0; p.beta = 1.0; p.lower = 1;
+    CUDA_TRY(gemm128(h, true, p, batch));
+    // 4.
+    rc = potrf_inv_rec(h, A, Li, sA, sLi, dInfo, off + n1, n2, batch);
+    if (rc) return rc;
+    // 5a. W2 = L21 * Li11     Bop[k][j] = Li11[k][j] != 0 only for k >= j
+    //     (L21 is read from the matrix: the W1 workspace was reused by the recursion in step 4)
+    memset(&p, 0, sizeof(p));
+    p.A = A21; p.lda = ld; p.sA = sA;
+    p.B = Li11; p.ldb = ld; p.sB = sLi;
+    p.C = h->dW2; p.ldc = n1; p.sC = sW;
+    p.mt = n2 / 128; p.nt = n1 / 128; p.K = n1; p.alpha = 1.0; p.beta = 0.0; p.kflags = GEMM_KJ_GE;
+    CUDA_TRY(gemm128(h, false, p, batch));
+    // 5b. Li21 = -Li22 * W2   A[i][k] = Li22[i][k] != 0 only for k <= i
+    memset(&p, 0, sizeof(p));
+    p.A = Li22; p.lda = ld; p.sA = sLi;
+    p.B = h->dW2; p.ldb = n1; p.sB = sW;
+    p.C = Li21; p.ldc = ld; p.sC = sLi;
+    p.mt = n2 / 128; p.nt = n1 / 128; p.K = n2; p.alpha = -1.0; p.beta = 0.0; p.kflags = GEMM_KI_LE;
+    CUDA_TRY(gemm128(h, false, p, batch));
+    return GPMPC_OK;
+}
+
+static int launch_kbuild(gpmpc_handle_t h, const double* dHyp, const double* dJit, double* K, int batch, int full)
+{
+    const int T = h->Npad / KB_TILE;
+    const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;
+    dim3 grid(T * (T + 1) / 2, 1, batch);
+    kbuild_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, dHyp, h->Nx + 2, dJit,
+                                               K, h->Npad, slab(h), full);
+    CUDA_TRY(cudaGetLastError());
+    return GPMPC_OK;
+}
+
+// alpha = Li^T (Li y) for `batch` consecutive local outputs starting at local index a
+static int launch_alpha(gpmpc_handle_t h, int a, int batch)
+{
+    const int n = h->Npad;
+    const double* Li = h->dLi + (long long)a * slab(h);
+    dim3 g1((n + 7) / 8, 1, batch);
+    trmv_lower_kernel<<<g1, 256, 0, h->st>>>(Li, n, slab(h), h->dY + (long long)a * n, n,
+                                              h->dTmp + (long long)a * n, n, n);
+    CUDA_TRY(cudaGetLastError());
+    dim3 g2(n / 32, 1, batch);
+    trmv_lower_T_kernel<<<g2, 256, 0, h->st>>>(Li, n, slab(h), h->dTmp + (long long)a * n, n,
+                                                h->dAlpha + (long long)a * n, n, n);
+    CUDA_TRY(cudaGetLastError());
+    logdet_dot_kernel<<<batch, 256, 0, h->st>>>(h->dL + (long long)a * slab(h), n, slab(h),
+                                                 h->dY + (long long)a * n, n,
+                                                 h->dAlpha + (long long)a * n, n, n, h->dRes + 2 * a);
+    CUDA_TRY(cudaGetLastError());
+    return GPMPC_OK;
+}
+
+// K(theta) -> L, Li for local output a with the reference's single jitter retry.
+// used: 0 ok, 1 jitter used, >1: 1 + failing pivot.  dHyp = device hyper row of that output.
+static int factor_one(gpmpc_handle_t h, int a, const double* dHyp, double jitter, int* used)
+{
+    double* L = h->dL + (long long)a * slab(h);
+    double* Li = h->dLi + (long long)a * slab(h);
+    *used = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const double jit = attempt ? jitter : 0.0;
+        CUDA_TRY(cudaMemcpyAsync(h->dJit + a, &jit, sizeof(double), cudaMemcpyHostToDevice, h->st));
+        CUDA_TRY(cudaMemsetAsync(h->dInfo + a, 0, sizeof(int), h->st));
+        // kbuild indexes hyper/jitter by blockIdx.z (== 0 here): pass row pointers
+        {
+            const int T = h->Npad / KB_TILE;
+            const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;
+            dim3 grid(T * (T + 1) / 2, 1, 1);
+            kbuild_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, dHyp, h->Nx + 2,
+                                                       h->dJit + a, L, h->Npad, slab(h), 0);
+            CUDA_TRY(cudaGetLastError());
+        }
+        int rc = potrf_inv_rec(h, L, Li, slab(h), slab(h), h->dInfo + a, 0, h->Npad, 1);
+        if (rc) return rc;
+        int info = 0;
+        CUDA_TRY(cudaMemcpyAsync(&info, h->dInfo + a, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (info == 0) { *used = attempt; return GPMPC_OK; }
+        *used = 1 + info;
+    }
+    return GPMPC_ERR_NOTPD;
+}
+
+// ------------------------------------------------------------------------------------
+extern "C" int gpmpc_version(void) { return GPMPC_VERSION; }
+
+extern "C" const char* gpmpc_last_error(gpmpc_handle_t h) { return h ? h->err : g_create_err; }
+
+#define ALLOC(ptr, count)                                                               \
+    do {                                                                                \
+        cudaError_t _e = cudaMalloc((void**)&(ptr), (size_t)(count) * sizeof(*(ptr)));  \
+        if (_e != cudaSuccess) {                                                        \
+            set_error(h, "cudaMalloc(%s, %zu bytes) failed: %s", #ptr,                  \
+                      (size_t)(count) * sizeof(*(ptr)), cudaGetErrorString(_e));        \
+            return GPMPC_ERR_CUDA;                                                      \
+        }                                                                               \
+        cudaMemsetAsync((ptr), 0, (size_t)(count) * sizeof(*(ptr)), h->st);             \
+    } while (0)
+
+extern "C" int gpmpc_create(int N, int Nx, int Ny, int out_begin, int out_count, int device, gpmpc_handle_t* out)
+{
+    gpmpc_handle_t h = nullptr;
+    if (!out) return GPMPC_ERR_ARG;
+    *out = nullptr;
+    if (N < 1 || Nx < 1 || Nx > NX_MAX || Ny < 1 || out_begin < 0 || out_count < 1 || out_begin + out_count > Ny) {
+        set_error(nullptr, "gpmpc_create: bad sizes N=%d Nx=%d (max %d) Ny=%d outputs [%d,%d)", N, Nx, NX_MAX, Ny,
+                  out_begin, out_begin + out_count);
+        return GPMPC_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) {
+        set_error(nullptr, "gpmpc_create: no usable CUDA device %d (count %d, %s) -- this engine has no CPU path",
+                  device, ndev, cudaGetErrorString(e));
+        return GPMPC_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        set_error(nullptr, "gpmpc_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                  prop.major, prop.minor);
+        return GPMPC_ERR_CUDA;
+    }
+    h = new gpmpc_handle_s();
+    h->N = N; h->Nx = Nx; h->Ny = Ny; h->a0 = out_begin; h->nloc = out_count; h->device = device;
+    h->nloc_max = out_count; h->world = 1; h->rank = 0;
+    h->Npad = (N + GPMPC_TILE - 1) / GPMPC_TILE * GPMPC_TILE;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    const long long np = h->Npad;
+    ALLOC(h->dXT, (long long)Nx * np);
+    ALLOC(h->dY, (long long)out_count * np);
+    ALLOC(h->dHyp, (long long)out_count * (Nx + 2));
+    ALLOC(h->dHypTmp, Nx + 2);
+    ALLOC(h->dJit, out_count);
+    ALLOC(h->dL, out_count * slab(h));
+    ALLOC(h->dLi, out_count * slab(h));
+    ALLOC(h->dW1, out_count * wslab(h));
+    ALLOC(h->dW2, out_count * wslab(h));
+    ALLOC(h->dAlpha, (long long)out_count * np);
+    ALLOC(h->dTmp, (long long)out_count * np);
+    ALLOC(h->dRes, 2 * out_count);
+    ALLOC(h->dInfo, out_count);
+    ALLOC(h->dGrad, Nx + 2);
+    h->hyper.assign((size_t)out_count * (Nx + 2), 0.0);
+    h->logdet.assign(out_count, 0.0); h->yalpha.assign(out_count, 0.0); h->jitter_used.assign(out_count, 0);
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    *out = h;
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_destroy(gpmpc_handle_t h)
+{
+    if (!h) return GPMPC_OK;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    double* bufs[] = {h->dXT, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
+                      h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dG, h->dZ, h->dSigma, h->dMean,
+                      h->dVar, h->dJ, h->dCov, h->dU, h->dKinv, h->dGradPart, h->dGrad};
+    for (double* b : bufs) if (b) cudaFree(b);
+    if (h->dInfo) cudaFree(h->dInfo);
+    if (h->hPinned) cudaFreeHost(h->hPinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return GPMPC_OK;
+}
+
+static int ensure_pinned(gpmpc_handle_t h, size_t bytes)
+{
+    if (h->hPinnedBytes >= bytes) return GPMPC_OK;
+    if (h->hPinned) cudaFreeHost(h->hPinned);
+    h->hPinned = nullptr; h->hPinnedBytes = 0;
+    CUDA_TRY(cudaMallocHost((void**)&h->hPinned, bytes));
+    h->hPinnedBytes = bytes;
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_set_data(gpmpc_handle_t h, const double* X, const double* Y)
+{
+    if (!h || !X || !Y) return GPMPC_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int N = h->N, Nx = h->Nx, np = h->Npad;
+    std::vector<double> xt((size_t)Nx * np, 0.0), yl((size_t)h->nloc * np, 0.0);
+    for (int i = 0; i < N; ++i)
+        for (int d = 0; d < Nx; ++d) xt[(size_t)d * np + i] = X[(size_t)i * Nx + d];
+    for (int a = 0; a < h->nloc; ++a)
+        for (int i = 0; i < N; ++i) yl[(size_t)a * np + i] = Y[(size_t)i * h->Ny + h->a0 + a];
+    CUDA_TRY(cudaMemcpyAsync(h->dXT, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CUDA_TRY(cudaMemcpyAsync(h->dY, yl.data(), yl.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    h->has_data = true; h->factorized = false;
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_set_hyper(gpmpc_handle_t h, const double* hyper, int ld)
+{
+    if (!h || !hyper || ld < h->Nx + 2) { if (h) set_error(h, "gpmpc_set_hyper: ld < Nx+2"); return GPMPC_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int m = h->Nx + 2;
+    for (int a = 0; a < h->nloc; ++a)
+        for (int q = 0; q < m; ++q) {
+            const double v = hyper[(size_t)(h->a0 + a) * ld + q];
+            if (q < h->Nx && v == 0.0) { set_error(h, "gpmpc_set_hyper: zero length scale"); return GPMPC_ERR_ARG; }
+            h->hyper[(size_t)a * m + q] = v;
+        }
+    CUDA_TRY(cudaMemcpyAsync(h->dHyp, h->hyper.data(), h->hyper.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    h->has_hyper = true; h->factorized = false;
+    return GPMPC_OK;
+}
+
+static int local_index(gpmpc_handle_t h, int a)
+{
+    if (a < h->a0 || a >= h->a0 + h->nloc) { set_error(h, "output %d is not owned by this handle [%d,%d)", a, h->a0, h->a0 + h->nloc); return -1; }
+    return a - h->a0;
+}
+
+static int ensure_nlml_scratch(gpmpc_handle_t h)
+{
+    if (!h->dU) { ALLOC(h->dU, slab(h)); }
+    if (!h->dKinv) { ALLOC(h->dKinv, slab(h)); }
+    if (!h->dGradPart) {
+        const int T = h->Npad / KB_TILE;
+        ALLOC(h->dGradPart, (long long)T * (T + 1) / 2 * (h->Nx + 2));
+    }
+    return GPMPC_OK;
+}
+
+static int extract_to_host(gpmpc_handle_t h, const double* src, double* dst, int mode)
+{
+    const int N = h->N;
+    if (!h->dKinv) { int rc = ensure_nlml_scratch(h); if (rc) return rc; }
+    // stage through dU (N*N fits: Npad >= N)
+    dim3 g((N + 127) / 128, N);
+    extract_kernel<<<g, 128, 0, h->st>>>(src, h->Npad, h->dU, N, mode);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dst, h->dU, (size_t)N * N * 8, cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_build_K(gpmpc_handle_t h, int a, double* K_out)
+{
+    if (!h) return GPMPC_ERR_ARG;
+    if (!h->has_data || !h->has_hyper) { set_error(h, "gpmpc_build_K: set_data and set_hyper first"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int al = local_index(h, a);
+    if (al < 0) return GPMPC_ERR_ARG;
+    int rc = ensure_nlml_scratch(h);
+    if (rc) return rc;
+    const double zero = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(h->dJit + al, &zero, 8, cudaMemcpyHostToDevice, h->st));
+    {
+        const int T = h->Npad / KB_TILE;
+        const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;
+        dim3 grid(T * (T + 1) / 2, 1, 1);
+        kbuild_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp + (long long)al * (h->Nx + 2),
+                                                   h->Nx + 2, h->dJit + al, h->dKinv, h->Npad, slab(h), 1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (K_out) return extract_to_host(h, h->dKinv, K_out, 0);
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_factorize(gpmpc_handle_t h, double jitter, int* info)
+{
+    if (!h) return GPMPC_ERR_ARG;
+    if (!h->has_data || !h->has_hyper) { set_error(h, "gpmpc_factorize: set_data and set_hyper first"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int nl = h->nloc;
+    CUDA_TRY(cudaMemsetAsync(h->dJit, 0, nl * sizeof(double), h->st));
+    CUDA_TRY(cudaMemsetAsync(h->dInfo, 0, nl * sizeof(int), h->st));
+    int rc = launch_kbuild(h, h->dHyp, h->dJit, h->dL, nl, 0);
+    if (rc) return rc;
+    rc = potrf_inv_rec(h, h->dL, h->dLi, slab(h), slab(h), h->dInfo, 0, h->Npad, nl);
+    if (rc) return rc;
+    std::vector<int> inf(nl, 0);
+    CUDA_TRY(cudaMemcpyAsync(inf.data(), h->dInfo, nl * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    int worst = GPMPC_OK;
+    for (int a = 0; a < nl; ++a) {
+        h->jitter_used[a] = 0;
+        if (inf[a] != 0) {      // optimize.py:483-488: add jitter once, retry, else propagate
+            int used = 0;
+            rc = factor_one(h, a, h->dHyp + (long long)a * (h->Nx + 2), jitter, &used);
+            h->jitter_used[a] = used;
+            if (rc == GPMPC_ERR_NOTPD) { worst = rc; set_error(h, "output %d: K not positive definite even with jitter %g (pivot %d)", h->a0 + a, jitter, used - 1); }
+            else if (rc) return rc;
+        }
+        if (info) info[a] = h->jitter_used[a];
+    }
+    if (worst) return worst;
+    rc = launch_alpha(h, 0, nl);
+    if (rc) return rc;
+    std::vector<double> res(2 * nl);
+    CUDA_TRY(cudaMemcpyAsync(res.data(), h->dRes, 2 * nl * 8, cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    for (int a = 0; a < nl; ++a) { h->logdet[a] = res[2 * a]; h->yalpha[a] = res[2 * a + 1]; }
+    h->factorized = true;
+    return GPMPC_OK;
+}
+
+// K^-1 (lower) of local output al into dKinv:  U = Li^T,  K^-1 = U U^T
+static int compute_kinv(gpmpc_handle_t h, int al)
+{
+    int rc = ensure_nlml_scratch(h);
+    if (rc) return rc;
+    const int np = h->Npad;
+    dim3 g(np / 32, np / 32), b(32, 8);
+    transpose_lower_kernel<<<g, b, 0, h->st>>>(h->dLi + (long long)al * slab(h), h->dU, np, np / 32);
+    CUDA_TRY(cudaGetLastError());
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.A = h->dU; p.lda = np; p.B = h->dU; p.ldb = np; p.C = h->dKinv; p.ldc = np;
+    p.mt = np / 128; p.nt = np / 128; p.K = np; p.alpha = 1.0; p.beta = 0.0;
+    p.kflags = GEMM_KI_GE | GEMM_KJ_GE; p.lower = 1;
+    CUDA_TRY(gemm128(h, true, p, 1));
+    return GPMPC_OK;
+}
+
+template <int NXP>
+static cudaError_t launch_grad(gpmpc_handle_t h, int al, const double* dHyp)
+{
+    const int T = h->Npad / KB_TILE;
+    const int smem = 2 * h->Nx * KB_TILE * 8;
+    nlml_grad_kernel<NXP><<<T * (T + 1) / 2, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, dHyp, h->dKinv, h->Npad,
+                                                                 h->dAlpha + (long long)al * h->Npad, h->dGradPart);
+    return cudaGetLastError();
+}
+
+extern "C" int gpmpc_nlml(gpmpc_handle_t h, int a, const double* theta, double* nll, double* grad)
+{
+    if (!h || !theta || !nll) return GPMPC_ERR_ARG;
+    if (!h->has_data) { set_error(h, "gpmpc_nlml: set_data first"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int al = local_index(h, a);
+    if (al < 0) return GPMPC_ERR_ARG;
+    const int m = h->Nx + 2;
+    for (int d = 0; d < h->Nx; ++d) if (theta[d] == 0.0) { set_error(h, "gpmpc_nlml: zero length scale"); return GPMPC_ERR_ARG; }
+    h->factorized = false;
+    CUDA_TRY(cudaMemcpyAsync(h->dHypTmp, theta, m * 8, cudaMemcpyHostToDevice, h->st));
+    int used = 0;
+    int rc = factor_one(h, al, h->dHypTmp, 1e-8, &used);     // optimize.py:345-350
+    if (rc) { if (rc == GPMPC_ERR_NOTPD) set_error(h, "gpmpc_nlml: K not positive definite even with jitter"); return rc; }
+    rc = launch_alpha(h, al, 1);
+    if (rc) return rc;
+    double res[2];
+    CUDA_TRY(cudaMemcpyAsync(res, h->dRes + 2 * al, 16, cudaMemcpyDeviceToHost, h->st));
+    if (grad) {
+        rc = compute_kinv(h, al);
+        if (rc) return rc;
+        cudaError_t e = (h->Nx <= 8) ? launch_grad<8>(h, al, h->dHypTmp)
+                      : (h->Nx <= 16) ? launch_grad<16>(h, al, h->dHypTmp) : launch_grad<32>(h, al, h->dHypTmp);
+        CUDA_TRY(e);
+        const int T = h->Npad / KB_TILE;
+        nlml_grad_final_kernel<<<m, 256, 0, h->st>>>(h->dGradPart, T * (T + 1) / 2, h->Nx, h->dHypTmp, h->dGrad);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(grad, h->dGrad, m * 8, cudaMemcpyDeviceToHost, h->st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    *nll = 0.5 * res[1] + 0.5 * res[0];                      // optimize.py:355
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_get(gpmpc_handle_t h, int what, int a, double* dst)
+{
+    if (!h || !dst) return GPMPC_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int al = local_index(h, a);
+    if (al < 0) return GPMPC_ERR_ARG;
+    if (what == GPMPC_GET_K) return gpmpc_build_K(h, a, dst);
+    if (!h->factorized) { set_error(h, "gpmpc_get: call gpmpc_factorize first"); return GPMPC_ERR_STATE; }
+    switch (what) {
+    case GPMPC_GET_CHOL: return extract_to_host(h, h->dL + (long long)al * slab(h), dst, 1);
+    case GPMPC_GET_LINV: return extract_to_host(h, h->dLi + (long long)al * slab(h), dst, 1);
+    case GPMPC_GET_ALPHA:
+        CUDA_TRY(cudaMemcpyAsync(dst, h->dAlpha + (long long)al * h->Npad, h->N * 8, cudaMemcpyDeviceToHost, h->st));
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        return GPMPC_OK;
+    case GPMPC_GET_LOGDET: dst[0] = h->logdet[al]; return GPMPC_OK;
+    case GPMPC_GET_INVK: {
+        int rc = compute_kinv(h, al);
+        if (rc) return rc;
+        // dKinv -> host through dU is not possible (dU is an input of compute_kinv but free now)
+        return extract_to_host(h, h->dKinv, dst, 2);
+    }
+    default: set_error(h, "gpmpc_get: unknown selector %d", what); return GPMPC_ERR_ARG;
+    }
+}
+
+extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value)
+{
+    if (!h || !name) return GPMPC_ERR_ARG;
+    if (!strcmp(name, "refine")) { h->opt_refine = value != 0.0; return GPMPC_OK; }
+    if (!strcmp(name, "ksplit")) {
+        const int v = (int)value;
+        if (v < 0 || v % 128) { set_error(h, "ksplit must be a non-negative multiple of 128"); return GPMPC_ERR_ARG; }
+        h->opt_ksplit = v; return GPMPC_OK;
+    }
+    set_error(h, "unknown option %s", name);
+    return GPMPC_ERR_ARG;
+}
+
+// ------------------------------------------------------------------------------------
+// predict
+// ------------------------------------------------------------------------------------
+static int ensure_predict_bufs(gpmpc_handle_t h, int H)
+{
+    const long long np = h->Npad;
+    if (!h->dKST) {
+        ALLOC(h->dKST, (long long)h->nloc * HB * np);
+        ALLOC(h->dPart, (long long)h->nloc * MAX_CHUNKS * HB * np);
+        ALLOC(h->dPMJ, (long long)h->nloc * HB * ((np + KS_CHUNK - 1) / KS_CHUNK) * (h->Nx + 1));
+        ALLOC(h->dSQ, (long long)h->nloc * HB * ((np + 255) / 256));
+    }
+    if (h->opt_refine && !h->dV) {
+        ALLOC(h->dV, (long long)h->nloc * HB * np);
+        ALLOC(h->dR, (long long)h->nloc * HB * np);
+    }
+    if (H > h->Hcap) {
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        double* bufs[] = {h->dG, h->dZ, h->dSigma, h->dMean, h->dVar, h->dJ, h->dCov};
+        for (double* b : bufs) if (b) cudaFree(b);
+        h->dG = h->dZ = h->dSigma = h->dMean = h->dVar = h->dJ = h->dCov = nullptr;
+        const int cap = std::max(H, HB);
+        const int nyp = h->nloc_max * h->world;
+        ALLOC(h->dG, (long long)nyp * cap * (h->Nx + 2));
+        ALLOC(h->dZ, (long long)cap * h->Nx);
+        ALLOC(h->dSigma, (long long)cap * h->Nx * h->Nx);
+        ALLOC(h->dMean, (long long)cap * h->Ny);
+        ALLOC(h->dVar, (long long)cap * h->Ny);
+        ALLOC(h->dJ, (long long)cap * h->Ny * h->Nx);
+        ALLOC(h->dCov, (long long)cap * h->Ny * h->Ny);
+        h->Hcap = cap;
+    }
+    return GPMPC_OK;
+}
+
+static int choose_ksplit(gpmpc_handle_t h)
+{
+    const int np = h->Npad, nt = np / 128;
+    if (h->opt_ksplit) return h->opt_ksplit >= np ? 0 : std::max(h->opt_ksplit, (np / MAX_CHUNKS + 127) / 128 * 128);
+    long long ks = (long long)h->nloc * nt * nt * 64 / 600;
+    ks = (ks + 127) / 128 * 128;
+    ks = std::max<long long>(ks, 256);
+    ks = std::max<long long>(ks, (np / MAX_CHUNKS + 127) / 128 * 128);
+    return ks >= np ? 0 : (int)ks;
+}
+
+template <int BM>
+static cudaError_t trigemm_bm(const GemmParams& p, int batch, int nch, cudaStream_t st)
+{
+    return gemm_launch<BM, 128, 1, 8, true>(p, batch, nch, st);
+}
+
+static cudaError_t trigemm_launch(int bm, const GemmParams& p, int batch, int nch, cudaStream_t st)
+{
+    switch (bm) {
+    case 8: return trigemm_bm<8>(p, batch, nch, st);
+    case 16: return trigemm_bm<16>(p, batch, nch, st);
+    case 24: return trigemm_bm<24>(p, batch, nch, st);
+    case 32: return trigemm_bm<32>(p, batch, nch, st);
+    case 40: return trigemm_bm<40>(p, batch, nch, st);
+    case 48: return trigemm_bm<48>(p, batch, nch, st);
+    case 56: return trigemm_bm<56>(p, batch, nch, st);
+    default: return trigemm_bm<64>(p, batch, nch, st);
+    }
+}
+
+template <int NXP>
+static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
+{
+    dim3 g(nblk, bm, h->nloc);
+    ks_mean_jac_kernel<NXP><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
+                                                   dZc, Hc, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
+    return cudaGetLastError();
+}
+
+// C = alpha * A(h-major rows) * T^T (+ Cin) with T = Li or L (lower), reduced over split-K
+// into `Vout` (may be null) and squared-norm partials into dSQ when sq != 0
+static int tri_product(gpmpc_handle_t h, const double* Amat, const double* T, int bm, int Hc, int ksplit,
+                       double* Vout)
+{
+    const int np = h->Npad;
+    const int nch = ksplit ? (np + ksplit - 1) / ksplit : 1;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.A = Amat; p.lda = np; p.sA = (long long)HB * np;
+    p.B = T; p.ldb = np; p.sB = slab(h);
+    p.C = h->dPart; p.ldc = np; p.sC = (long long)MAX_CHUNKS * HB * np;
+    p.mt = 1; p.nt = np / 128; p.K = np; p.alpha = 1.0; p.beta = 0.0; p.kflags = GEMM_KJ_LE;
+    p.ksplit = ksplit; p.sPart = (long long)HB * np;
+    CUDA_TRY(trigemm_launch(bm, p, h->nloc, nch, h->st));
+    const int nblk_sq = (np + 255) / 256;
+    dim3 g(nblk_sq, Hc, h->nloc);
+    reduce_sq_kernel<<<g, 256, 0, h->st>>>(h->dPart, np, (long long)HB * np, (long long)MAX_CHUNKS * HB * np, ksplit, np, Hc,
+                                            h->dSQ, nblk_sq, Vout, (long long)HB * np);
+    CUDA_TRY(cudaGetLastError());
+    return GPMPC_OK;
+}
+
+// r = ks - L v   (elementwise epilogue of the refinement residual) and v += dv
+__global__ void axpby_rows_kernel(const double* __restrict__ x, const double* __restrict__ y, double a, double b,
+                                  double* __restrict__ out, long long rowlen, long long srow, int rows)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y, bz = blockIdx.z;
+    if (i >= rowlen || r >= rows) return;
+    const long long o = (long long)bz * srow + (long long)r * rowlen + i;
+    out[o] = a * x[o] + b * y[o];
+}
+
+static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, const double* dSigma, int spp,
+                        double* d_mean, double* d_var, double* d_cov, double* d_jac)
+{
+    const int np = h->Npad, Nx = h->Nx;
+    const int ksplit = choose_ksplit(h);
+    const int nblk_mj = (np + KS_CHUNK - 1) / KS_CHUNK, nblk_sq = (np + 255) / 256;
+    for (int h0 = 0; h0 < H; h0 += HB) {
+        const int Hc = std::min(HB, H - h0);
+        const int bm = (Hc + 7) / 8 * 8;
+        const double* dZc = dZ + (long long)h0 * Nx;
+        cudaError_t e = (Nx <= 8) ? launch_ks<8>(h, dZc, Hc, bm, nblk_mj)
+                      : (Nx <= 16) ? launch_ks<16>(h, dZc, Hc, bm, nblk_mj) : launch_ks<32>(h, dZc, Hc, bm, nblk_mj);
+        CUDA_TRY(e);
+        if (!h->opt_refine) {
+            int rc = tri_product(h, h->dKST, h->dLi, bm, Hc, ksplit, nullptr);
+            if (rc) return rc;
+        } else {
+            // v1 = Li ks ; r = ks - L v1 ; v = v1 + Li r   (one step of iterative refinement)
+            int rc = tri_product(h, h->dKST, h->dLi, bm, Hc, ksplit, h->dV);
+            if (rc) return rc;
+            rc = tri_product(h, h->dV, h->dL, bm, Hc, ksplit, h->dR);          // dR = L v1
+            if (rc) return rc;
+            dim3 g((np + 255) / 256, bm, h->nloc);
+            axpby_rows_kernel<<<g, 256, 0, h->st>>>(h->dKST, h->dR, 1.0, -1.0, h->dR, np, (long long)HB * np, bm);
+            CUDA_TRY(cudaGetLastError());
+            rc = tri_product(h, h->dR, h->dLi, bm, Hc, ksplit, h->dR);         // dR = Li r
+            if (rc) return rc;
+            axpby_rows_kernel<<<g, 256, 0, h->st>>>(h->dV, h->dR, 1.0, 1.0, h->dV, np, (long long)HB * np, bm);
+            CUDA_TRY(cudaGetLastError());
+            // squared norms of the refined v: reuse the reducer with a single "chunk" = dV itself
+            dim3 g2(nblk_sq, Hc, h->nloc);
+            reduce_sq_kernel<<<g2, 256, 0, h->st>>>(h->dV, np, 0, (long long)HB * np, 0, np, Hc, h->dSQ, nblk_sq, nullptr, 0);
+            CUDA_TRY(cudaGetLastError());
+        }
+        dim3 gf(Hc, h->nloc);
+        finalize_local_kernel<<<gf, 64, 0, h->st>>>(h->dPMJ, nblk_mj, h->dSQ, nblk_sq, h->dHyp, Nx + 2, Nx, Hc,
+                                                     h->dG, h->a0, H, h0);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (h->world > 1) {
+        const size_t cnt = (size_t)h->nloc_max * H * (Nx + 2);
+        int r = g_nccl.AllGather(h->dG + (size_t)h->rank * cnt, h->dG, cnt, 8 /* ncclFloat64 */, h->comm, h->st);
+        if (r) { set_error(h, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GPMPC_ERR_NCCL; }
+    }
+    const int smem = (2 * h->Ny * Nx + h->Ny) * 8;
+    assemble_kernel<<<H, 128, smem, h->st>>>(h->dG, h->Ny, Nx, H, method == GPMPC_METHOD_TA, dSigma, spp,
+                                              d_mean, d_var, d_jac, d_cov);
+    CUDA_TRY(cudaGetLastError());
+    return GPMPC_OK;
+}
+
+static int predict_check(gpmpc_handle_t h, int method, int H)
+{
+    if (!h) return GPMPC_ERR_ARG;
+    if (!h->factorized) { set_error(h, "gpmpc_predict: call gpmpc_factorize first"); return GPMPC_ERR_STATE; }
+    if (H < 1) { set_error(h, "gpmpc_predict: H < 1"); return GPMPC_ERR_ARG; }
+    if (method != GPMPC_METHOD_ME && method != GPMPC_METHOD_TA) { set_error(h, "gpmpc_predict: unknown method %d", method); return GPMPC_ERR_ARG; }
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_predict_device(gpmpc_handle_t h, int method, int H, const double* dZ, const double* dSigma,
+                                    int spp, double* d_mean, double* d_var, double* d_cov, double* d_jac, int sync)
+{
+    int rc = predict_check(h, method, H);
+    if (rc) return rc;
+    if (!dZ || (method == GPMPC_METHOD_TA && d_cov && !dSigma)) { set_error(h, "gpmpc_predict_device: null Z / Sigma"); return GPMPC_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    rc = ensure_predict_bufs(h, H);
+    if (rc) return rc;
+    rc = predict_core(h, method, H, dZ, dSigma, spp, d_mean, d_var, d_cov, d_jac);
+    if (rc) return rc;
+    if (sync) CUDA_TRY(cudaStreamSynchronize(h->st));
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* Z, const double* Sigma,
+                             int spp, double* mean, double* var, double* cov, double* jac)
+{
+    int rc = predict_check(h, method, H);
+    if (rc) return rc;
+    if (!Z || (method == GPMPC_METHOD_TA && cov && !Sigma)) { set_error(h, "gpmpc_predict: null Z / Sigma"); return GPMPC_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    rc = ensure_predict_bufs(h, H);
+    if (rc) return rc;
+    const int Nx = h->Nx, Ny = h->Ny;
+    const size_t nz = (size_t)H * Nx, ns = (method == GPMPC_METHOD_TA && Sigma) ? (size_t)(spp ? H : 1) * Nx * Nx : 0;
+    const size_t nm = (size_t)H * Ny, nj = (size_t)H * Ny * Nx, nc = (size_t)H * Ny * Ny;
+    rc = ensure_pinned(h, (nz + ns + 2 * nm + nj + nc) * 8);
+    if (rc) return rc;
+    double* pin = h->hPinned;
+    memcpy(pin, Z, nz * 8);
+    if (ns) memcpy(pin + nz, Sigma, ns * 8);
+    CUDA_TRY(cudaMemcpyAsync(h->dZ, pin, nz * 8, cudaMemcpyHostToDevice, h->st));
+    if (ns) CUDA_TRY(cudaMemcpyAsync(h->dSigma, pin + nz, ns * 8, cudaMemcpyHostToDevice, h->st));
+    rc = predict_core(h, method, H, h->dZ, h->dSigma, spp, mean ? h->dMean : nullptr, var ? h->dVar : nullptr,
+                      cov ? h->dCov : nullptr, jac ? h->dJ : nullptr);
+    if (rc) return rc;
+    double* po = pin + nz + ns;
+    if (mean) CUDA_TRY(cudaMemcpyAsync(po, h->dMean, nm * 8, cudaMemcpyDeviceToHost, h->st));
+    if (var) CUDA_TRY(cudaMemcpyAsync(po + nm, h->dVar, nm * 8, cudaMemcpyDeviceToHost, h->st));
+    if (jac) CUDA_TRY(cudaMemcpyAsync(po + 2 * nm, h->dJ, nj * 8, cudaMemcpyDeviceToHost, h->st));
+    if (cov) CUDA_TRY(cudaMemcpyAsync(po + 2 * nm + nj, h->dCov, nc * 8, cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    if (mean) memcpy(mean, po, nm * 8);
+    if (var) memcpy(var, po + nm, nm * 8);
+    if (jac) memcpy(jac, po + 2 * nm, nj * 8);
+    if (cov) memcpy(cov, po + 2 * nm + nj, nc * 8);
+    return GPMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// multi-GPU
+// ------------------------------------------------------------------------------------
+extern "C" int gpmpc_comm_unique_id(void* id128)
+{
+    if (!id128) return GPMPC_ERR_ARG;
+    if (!nccl_load(g_create_err, sizeof(g_create_err))) return GPMPC_ERR_NCCL;
+    nccl_uid_t id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r) { snprintf(g_create_err, sizeof(g_create_err), "ncclGetUniqueId failed (%d)", r); return GPMPC_ERR_NCCL; }
+    memcpy(id128, &id, 128);
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_comm_init(gpmpc_handle_t h, const void* id128, int rank, int world)
+{
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return GPMPC_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int nlm = (h->Ny + world - 1) / world;
+    if (h->a0 != std::min(h->Ny, rank * nlm) || h->nloc > nlm) {
+        set_error(h, "gpmpc_comm_init: rank %d of %d must own outputs starting at %d (at most %d); handle owns [%d,%d)",
+                  rank, world, rank * nlm, nlm, h->a0, h->a0 + h->nloc);
+        return GPMPC_ERR_ARG;
+    }
+    if (world > 1) {
+        if (!nccl_load(h->err, sizeof(h->err))) return GPMPC_ERR_NCCL;
+        nccl_uid_t id;
+        memcpy(&id, id128, 128);
+        int r = g_nccl.CommInitRank(&h->comm, world, id, rank);
+        if (r) { set_error(h, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GPMPC_ERR_NCCL; }
+    }
+    h->rank = rank; h->world = world; h->nloc_max = nlm;
+    h->Hcap = 0;      // gather buffer must be re-sized for the padded output count
+    return GPMPC_OK;
+}
+
+extern "C" void* gpmpc_stream(gpmpc_handle_t h) { return h ? (void*)h->st : nullptr; }
+
+extern "C" int gpmpc_synchronize(gpmpc_handle_t h)
+{
+    if (!h) return GPMPC_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return GPMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// kernel-level timing for the roofline report (CUDA events on the handle's stream)
+// ------------------------------------------------------------------------------------
+extern "C" int gpmpc_profile(gpmpc_handle_t h, int what, int n, int reps, double* ms_out)
+{
+    if (!h || !ms_out || reps < 1) return GPMPC_ERR_ARG;
+    if (!h->has_data || !h->has_hyper) { set_error(h, "gpmpc_profile: set_data and set_hyper first"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int np = h->Npad;
+    float ms = 0.f;
+    int rc = GPMPC_OK;
+    auto run = [&](int rep) -> int {
+        switch (what) {
+        case GPMPC_PROF_KBUILD_FULL: return launch_kbuild(h, h->dHyp, h->dJit, h->dL, 1, 1);
+        case GPMPC_PROF_KBUILD_LOWER: return launch_kbuild(h, h->dHyp, h->dJit, h->dL, 1, 0);
+        case GPMPC_PROF_SYRK: {
+            // trailing update shape of the top recursion level: C(n2 x n2, lower) -= P P^T, K = n1
+            const int nn = (n > 0 && n <= np) ? n / 128 * 128 : np;
+            const int n1 = (nn / 128 / 2) * 128, n2 = nn - n1;
+            if (n1 < 128) { set_error(h, "gpmpc_profile: SYRK needs N >= 256"); return GPMPC_ERR_ARG; }
+            GemmParams p;
+            memset(&p, 0, sizeof(p));
+            p.A = h->dW1; p.lda = n1; p.B = h->dW1; p.ldb = n1;
+            p.C = h->dLi; p.ldc = np; p.Cin = h->dLi; p.ldcin = np;
+            p.mt = n2 / 128; p.nt = n2 / 128; p.K = n1; p.alpha = -1e-30; p.beta = 1.0; p.lower = 1;
+            cudaError_t e = gemm128(h, true, p, 1);
+            if (e != cudaSuccess) { set_error(h, "profile syrk: %s", cudaGetErrorString(e)); return GPMPC_ERR_CUDA; }
+            return GPMPC_OK;
+        }
+        case GPMPC_PROF_FACTORIZE: {
+            int r = launch_kbuild(h, h->dHyp, h->dJit, h->dL, 1, 0);
+            if (r) return r;
+            return potrf_inv_rec(h, h->dL, h->dLi, slab(h), slab(h), h->dInfo, 0, np, 1);
+        }
+        case GPMPC_PROF_TRIGEMM: {
+            const int Hc = (n > 0 && n <= HB) ? n : 56;
+            return tri_product(h, h->dKST, h->dLi, (Hc + 7) / 8 * 8, Hc, choose_ksplit(h), nullptr);
+        }
+        default: set_error(h, "gpmpc_profile: unknown selector %d", what); return GPMPC_ERR_ARG;
+        }
+    };
+    if (what == GPMPC_PROF_TRIGEMM) { rc = ensure_predict_bufs(h, HB); if (rc) return rc; }
+    CUDA_TRY(cudaMemsetAsync(h->dJit, 0, h->nloc * sizeof(double), h->st));
+    rc = run(-1);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    CUDA_TRY(cudaEventRecord(h->ev0, h->st));
+    for (int r = 0; r < reps; ++r) { rc = run(r); if (rc) return rc; }
+    CUDA_TRY(cudaEventRecord(h->ev1, h->st));
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    ms_out[0] = (double)ms / reps;
+    if (what != GPMPC_PROF_TRIGEMM) h->factorized = false;   // slabs were used as scratch
+    return GPMPC_OK;
+}

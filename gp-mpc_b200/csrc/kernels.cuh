@@ -1,0 +1,556 @@
+// Device kernels of the GP hot path other than the DMMA GEMM family.
+// Reference semantics are cited as file:line of helgeanl/GP-MPC.
+#pragma once
+#include "common.cuh"
+
+// hyper layout per output (device copy): [ell_0..ell_{Nx-1}, sf, sn]  (gp_class.py:139-142)
+#define KB_TILE 64
+
+// ---------------------------------------------------------------------------------------
+// a1/a2  K = sf2 * exp(-1/2 sum_d ((x_id - x_jd)/ell_d)^2) + (sn2 + jitter) I
+//   gp_functions.py:17-22 (direct differences), optimize.py:342-344 (noise + symmetrise:
+//   the direct-difference form is exactly symmetric, so (K+K^T)/2 is the identity map).
+//   XT is the d-major copy of X: XT[d*ldx + i].  One CTA computes one 64x64 tile of the
+//   lower triangle and (full mode) also stores its transpose through shared memory, so
+//   each exp is evaluated once for two outputs.  Rows/cols >= N get the identity tail.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+kbuild_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
+              const double* __restrict__ hyp, int hyp_ld, const double* __restrict__ jitter,
+              double* __restrict__ K, int ld, long long sK, int full)
+{
+    extern __shared__ double sm[];
+    double* Xi = sm;                       // [Nx][64] scaled by 1/ell
+    double* Xj = sm + Nx * KB_TILE;        // [Nx][64]
+    double* T = sm + 2 * Nx * KB_TILE;     // [64][65] transpose staging
+
+    const int a = blockIdx.z;
+    const double* hp = hyp + (long long)a * hyp_ld;
+    const int tt = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
+    while (bi * (bi + 1) / 2 > tt) --bi;
+    while ((bi + 1) * (bi + 2) / 2 <= tt) ++bi;
+    const int bj = tt - bi * (bi + 1) / 2;
+    const int i0 = bi * KB_TILE, j0 = bj * KB_TILE;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+    for (int idx = tid; idx < Nx * KB_TILE; idx += 256) {
+        const int d = idx / KB_TILE, r = idx % KB_TILE;
+        const double inv = 1.0 / hp[d];
+        Xi[idx] = XT[(long long)d * ldx + i0 + r] * inv;
+        Xj[idx] = XT[(long long)d * ldx + j0 + r] * inv;
+    }
+    __syncthreads();
+
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    for (int d = 0; d < Nx; ++d) {
+        double xi[4], xj[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xi[r] = Xi[d * KB_TILE + ty + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xj[c] = Xj[d * KB_TILE + tx + 16 * c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const double df = xi[r] - xj[c]; acc[r][c] = fma(df, df, acc[r][c]); }
+    }
+    const double sf2 = hp[Nx] * hp[Nx];
+    const double dg = hp[Nx + 1] * hp[Nx + 1] + (jitter ? jitter[a] : 0.0);
+    double* Ka = K + (long long)a * sK;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = i0 + ty + 16 * r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int col = j0 + tx + 16 * c;
+            double v;
+            if (row < N && col < N) {
+                v = sf2 * exp(-0.5 * acc[r][c]);
+                if (row == col) v += dg;
+            } else {
+                v = (row == col) ? 1.0 : 0.0;
+            }
+            acc[r][c] = v;
+            Ka[(long long)row * ld + col] = v;
+        }
+    }
+    if (full && bi != bj) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) T[(tx + 16 * c) * (KB_TILE + 1) + ty + 16 * r] = acc[r][c];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                Ka[(long long)(j0 + ty + 16 * r) * ld + i0 + tx + 16 * c] = T[(ty + 16 * r) * (KB_TILE + 1) + tx + 16 * c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// a3 leaf: 128x128 diagonal block  ->  L (in place, zeros above the diagonal) and L^-1.
+//   np.linalg.cholesky at optimize.py:346/485; a non-positive pivot is reported LAPACK
+//   style (1-based global index) so the host can apply the reference's single 1e-8
+//   jitter retry (optimize.py:347-350).  One CTA per batch entry; whole block in smem.
+// ---------------------------------------------------------------------------------------
+#define LEAF_N 128
+#define LEAF_LD 129
+__global__ void __launch_bounds__(256, 1)
+leaf_potrf_trtri_kernel(double* __restrict__ A, int lda, long long sA,
+                        double* __restrict__ Li, int ldi, long long sLi,
+                        int* __restrict__ info, int info_base)
+{
+    extern __shared__ double S[];           // [128][129]
+    __shared__ double colbuf[LEAF_N];
+    const int tid = threadIdx.x;
+    double* Ab = A + (long long)blockIdx.x * sA;
+    double* Lb = Li + (long long)blockIdx.x * sLi;
+    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
+        const int r = idx >> 7, c = idx & 127;
+        S[r * LEAF_LD + c] = Ab[(long long)r * lda + c];
+    }
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;
+    for (int j = 0; j < LEAF_N; ++j) {
+        const double d = S[j * LEAF_LD + j];
+        if (!(d > 0.0) && tid == 0) atomicCAS(info + blockIdx.x, 0, info_base + j + 1);
+        const double dj = sqrt(d);
+        const double inv = 1.0 / dj;
+        __syncthreads();                    // everyone has read the pivot
+        if (tid < LEAF_N) {
+            if (tid == j) S[j * LEAF_LD + j] = dj;
+            else if (tid > j) S[tid * LEAF_LD + j] *= inv;
+        }
+        __syncthreads();
+        for (int i = j + 1 + ty; i < LEAF_N; i += 16) {
+            const double lij = S[i * LEAF_LD + j];
+            for (int k = j + 1 + tx; k <= i; k += 16)
+                S[i * LEAF_LD + k] = fma(-lij, S[k * LEAF_LD + j], S[i * LEAF_LD + k]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
+        const int r = idx >> 7, c = idx & 127;
+        Ab[(long long)r * lda + c] = (c <= r) ? S[r * LEAF_LD + c] : 0.0;
+    }
+    // in-place lower-triangular inverse, last column first:
+    //   Linv[j][j] = 1/L[j][j];  Linv[i][j] = -Linv[j][j] * sum_{k=j+1..i} Linv[i][k] * L[k][j]
+    for (int j = LEAF_N - 1; j >= 0; --j) {
+        if (tid < LEAF_N && tid > j) colbuf[tid] = S[tid * LEAF_LD + j];
+        const double djj = 1.0 / S[j * LEAF_LD + j];
+        __syncthreads();
+        const int i = j + 1 + (tid >> 1);
+        double s0 = 0.0, s1 = 0.0;
+        if (i < LEAF_N) {
+            int k = j + 1 + (tid & 1);
+            for (; k + 2 <= i; k += 4) {
+                s0 = fma(S[i * LEAF_LD + k], colbuf[k], s0);
+                s1 = fma(S[i * LEAF_LD + k + 2], colbuf[k + 2], s1);
+            }
+            if (k <= i) s0 = fma(S[i * LEAF_LD + k], colbuf[k], s0);
+        }
+        double s = s0 + s1;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        __syncthreads();
+        if (i < LEAF_N && (tid & 1) == 0) S[i * LEAF_LD + j] = -djj * s;
+        if (tid == 0) S[j * LEAF_LD + j] = djj;
+        __syncthreads();
+    }
+    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
+        const int r = idx >> 7, c = idx & 127;
+        Lb[(long long)r * ldi + c] = (c <= r) ? S[r * LEAF_LD + c] : 0.0;
+    }
+}
+
+// batched 2-D copy  dst[b][r][c] = src[b][r][c]   (cols multiple of 2, 16-byte aligned)
+__global__ void copy2d_kernel(const double* __restrict__ src, int lds, long long ss,
+                              double* __restrict__ dst, int ldd, long long sd, int rows, int cols)
+{
+    const double* s = src + (long long)blockIdx.z * ss;
+    double* d = dst + (long long)blockIdx.z * sd;
+    const int c2 = cols >> 1;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < c2; c += gridDim.x * blockDim.x)
+            reinterpret_cast<double2*>(d + (long long)r * ldd)[c] =
+                reinterpret_cast<const double2*>(s + (long long)r * lds)[c];
+}
+
+// U = Linv^T for the lower tiles of Linv (32x32 smem transpose); U's strictly lower
+// tiles are never written and stay zero from allocation.
+__global__ void transpose_lower_kernel(const double* __restrict__ Li, double* __restrict__ U, int ld, int nt32)
+{
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = Li[(long long)(bi * 32 + r) * ld + bj * 32 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) U[(long long)(bj * 32 + r) * ld + bi * 32 + tx] = tile[tx][r];
+}
+
+// w = T * y with T lower-triangular (one warp per row).   a5: alpha = L^-T (L^-1 y)
+__global__ void trmv_lower_kernel(const double* __restrict__ T, int ld, long long sT,
+                                  const double* __restrict__ y, long long sy,
+                                  double* __restrict__ w, long long sw, int n)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double* Tr = T + (long long)blockIdx.z * sT + (long long)row * ld;
+    const double* yy = y + (long long)blockIdx.z * sy;
+    double s = 0.0;
+    for (int k = lane; k <= row; k += 32) s = fma(Tr[k], yy[k], s);
+    s = warp_sum(s);
+    if (lane == 0) w[(long long)blockIdx.z * sw + row] = s;
+}
+
+// out = T^T * w with T lower-triangular: out[k] = sum_{i>=k} T[i][k] w[i]; 32 columns per CTA
+__global__ void __launch_bounds__(256)
+trmv_lower_T_kernel(const double* __restrict__ T, int ld, long long sT,
+                    const double* __restrict__ w, long long sw,
+                    double* __restrict__ out, long long so, int n)
+{
+    __shared__ double red[8][33];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + lane;
+    const double* Tb = T + (long long)blockIdx.z * sT;
+    const double* ww = w + (long long)blockIdx.z * sw;
+    double s = 0.0;
+    for (int i = blockIdx.x * 32 + wp; i < n; i += 8)
+        if (i >= k) s = fma(Tb[(long long)i * ld + k], ww[i], s);
+    red[wp][lane] = s;
+    __syncthreads();
+    if (wp == 0) {
+        double r = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r += red[q][lane];
+        out[(long long)blockIdx.z * so + k] = r;
+    }
+}
+
+// per batch entry: res[0] = sum_i log(L_ii) * 2 (a4, optimize.py:352), res[1] = y . alpha
+__global__ void __launch_bounds__(256)
+logdet_dot_kernel(const double* __restrict__ L, int ld, long long sL,
+                  const double* __restrict__ y, long long sy,
+                  const double* __restrict__ al, long long sal, int n, double* __restrict__ res)
+{
+    __shared__ double r0[8], r1[8];
+    const double* Lb = L + (long long)blockIdx.x * sL;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        s0 += log(fabs(Lb[(long long)i * ld + i]));
+        s1 = fma(y[(long long)blockIdx.x * sy + i], al[(long long)blockIdx.x * sal + i], s1);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = s0; r1[threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < 8; ++q) { a += r0[q]; b += r1[q]; }
+        res[2 * blockIdx.x] = 2.0 * a;
+        res[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// a8/a9 stage 1: ks, partial mean and partial Jacobian for every (output, test point).
+//   ks_i = covSE(X_i, z)               gp_functions.py:114-117,132
+//   mean = ks^T alpha                  gp_functions.py:119-120,135
+//   J_d  = sum_i alpha_i ks_i (X_id - z_d)/ell_d^2   (closed form of ca.jacobian, :146-147)
+//   KST[a][h][i] (h-major) is the B^T operand of the v = Linv ks tensor-core product.
+//   grid (Npad/1024, BM rows, outputs); rows h >= H are zero-filled.
+// ---------------------------------------------------------------------------------------
+#define KS_CHUNK 1024
+template <int NXP>
+__global__ void __launch_bounds__(256)
+ks_mean_jac_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
+                   const double* __restrict__ hyp, int hyp_ld,
+                   const double* __restrict__ alpha, long long sal,
+                   const double* __restrict__ Z, int H,
+                   double* __restrict__ KST, int ldk, long long sK,
+                   double* __restrict__ PMJ, int nblk)
+{
+    __shared__ double red[8][NXP + 1];
+    __shared__ double zs[NXP], ie[NXP], ie2[NXP];
+    const int a = blockIdx.z, h = blockIdx.y, blk = blockIdx.x;
+    const int tid = threadIdx.x;
+    double* krow = KST + (long long)a * sK + (long long)h * ldk;
+    if (h >= H) {
+        for (int q = 0; q < KS_CHUNK / 256; ++q) {
+            const int i = blk * KS_CHUNK + tid + 256 * q;
+            if (i < ldk) krow[i] = 0.0;
+        }
+        return;
+    }
+    const double* hp = hyp + (long long)a * hyp_ld;
+    if (tid < NXP) {
+        const double e = (tid < Nx) ? hp[tid] : 1.0;
+        zs[tid] = (tid < Nx) ? Z[(long long)h * Nx + tid] : 0.0;
+        ie[tid] = 1.0 / e;
+        ie2[tid] = 1.0 / (e * e);
+    }
+    __syncthreads();
+    const double sf2 = hp[Nx] * hp[Nx];
+    double am = 0.0, aj[NXP];
+#pragma unroll
+    for (int d = 0; d < NXP; ++d) aj[d] = 0.0;
+    const double* al = alpha + (long long)a * sal;
+    for (int q = 0; q < KS_CHUNK / 256; ++q) {
+        const int i = blk * KS_CHUNK + tid + 256 * q;
+        double ks = 0.0;
+        if (i < N) {
+            double dist = 0.0, df[NXP];
+#pragma unroll
+            for (int d = 0; d < NXP; ++d) {
+                df[d] = 0.0;
+                if (d < Nx) {
+                    df[d] = XT[(long long)d * ldx + i] - zs[d];
+                    const double s = df[d] * ie[d];
+                    dist = fma(s, s, dist);
+                }
+            }
+            ks = sf2 * exp(-0.5 * dist);
+            const double w = al[i] * ks;
+            am += w;
+#pragma unroll
+            for (int d = 0; d < NXP; ++d) aj[d] = fma(w, df[d], aj[d]);
+        }
+        if (i < ldk) krow[i] = ks;
+    }
+    am = warp_sum(am);
+#pragma unroll
+    for (int d = 0; d < NXP; ++d) aj[d] = warp_sum(aj[d]);
+    if ((tid & 31) == 0) {
+        red[tid >> 5][0] = am;
+#pragma unroll
+        for (int d = 0; d < NXP; ++d) red[tid >> 5][d + 1] = aj[d];
+    }
+    __syncthreads();
+    if (tid <= Nx) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += red[q][tid];
+        if (tid > 0) s *= ie2[tid - 1];
+        PMJ[(((long long)a * H + h) * nblk + blk) * (Nx + 1) + tid] = s;
+    }
+}
+
+// stage 3: v_i = sum over valid split-K chunks; partial column norms  sum_i v_i^2
+//   (var = sf2 - v^T v, gp_functions.py:125-126,136).  grid (Npad/256, H, outputs)
+__global__ void __launch_bounds__(256)
+reduce_sq_kernel(const double* __restrict__ Part, int ldp, long long sPart, long long sPa,
+                 int ksplit, int Kdim, int H, double* __restrict__ SQ, int nblk,
+                 double* __restrict__ Vout, long long sV)
+{
+    __shared__ double red[8];
+    const int a = blockIdx.z, h = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    int nch = 1;
+    if (ksplit) {
+        const int khi = min(Kdim, ((i >> 7) + 1) * 128);
+        nch = (khi + ksplit - 1) / ksplit;
+    }
+    const double* p = Part + (long long)a * sPa + (long long)h * ldp + i;
+    double v = 0.0;
+    if (i < Kdim) {
+        for (int c = 0; c < nch; ++c) v += p[(long long)c * sPart];
+        if (Vout) Vout[(long long)a * sV + (long long)h * ldp + i] = v;
+    }
+    double s = warp_sum(v * v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int q = 0; q < 8; ++q) r += red[q];
+        SQ[((long long)a * H + h) * nblk + blockIdx.x] = r;
+    }
+}
+
+// stage 4: per local output and test point: [mean, var, J_0..J_{Nx-1}] into the gather
+// buffer G[slot][h][2+Nx]  (slot = global output index; one contiguous chunk per rank)
+__global__ void finalize_local_kernel(const double* __restrict__ PMJ, int nblk_mj,
+                                      const double* __restrict__ SQ, int nblk_sq,
+                                      const double* __restrict__ hyp, int hyp_ld, int Nx, int Hc,
+                                      double* __restrict__ G, int slot0, int Htot, int h0)
+{
+    const int a = blockIdx.y, h = blockIdx.x, q = threadIdx.x;   // q in [0, Nx+1]
+    if (q > Nx + 1) return;
+    double* out = G + (((long long)(slot0 + a)) * Htot + h0 + h) * (Nx + 2);
+    if (q <= Nx) {
+        const double* p = PMJ + (((long long)a * Hc + h) * nblk_mj) * (Nx + 1) + q;
+        double s = 0.0;
+        for (int b = 0; b < nblk_mj; ++b) s += p[(long long)b * (Nx + 1)];
+        out[q == 0 ? 0 : q + 1] = s;
+    } else {
+        const double* p = SQ + ((long long)a * Hc + h) * nblk_sq;
+        double s = 0.0;
+        for (int b = 0; b < nblk_sq; ++b) s += p[b];
+        const double sf = hyp[(long long)a * hyp_ld + Nx];
+        out[1] = sf * sf - s;
+    }
+}
+
+// stage 5 (after the all-gather): assemble mean (H,Ny), var (H,Ny), J (H,Ny,Nx) and the
+// covariance: 'ME' diag(var) (gp_functions.py:142); 'TA' diag(var) + J Sigma J^T
+// (build_TA_cov, gp_functions.py:167-171).  sigma_per_point: Sigma is (H,Nx,Nx).
+__global__ void assemble_kernel(const double* __restrict__ G, int Ny, int Nx, int H, int method_ta,
+                                const double* __restrict__ Sigma, int sigma_per_point,
+                                double* __restrict__ mean, double* __restrict__ var,
+                                double* __restrict__ J, double* __restrict__ cov)
+{
+    extern __shared__ double sh[];          // Jh[Ny][Nx], JS[Ny][Nx], varh[Ny]
+    double* Jh = sh; double* JS = sh + Ny * Nx; double* vh = sh + 2 * Ny * Nx;
+    const int h = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+    for (int idx = tid; idx < Ny * Nx; idx += nth) {
+        const int a = idx / Nx, d = idx % Nx;
+        const double v = G[(((long long)a) * H + h) * (Nx + 2) + 2 + d];
+        Jh[idx] = v;
+        if (J) J[((long long)h * Ny + a) * Nx + d] = v;
+    }
+    for (int a = tid; a < Ny; a += nth) {
+        const double* g = G + (((long long)a) * H + h) * (Nx + 2);
+        if (mean) mean[(long long)h * Ny + a] = g[0];
+        if (var) var[(long long)h * Ny + a] = g[1];
+        vh[a] = g[1];
+    }
+    __syncthreads();
+    if (!cov) return;
+    if (method_ta) {
+        const double* Sg = Sigma + (sigma_per_point ? (long long)h * Nx * Nx : 0);
+        for (int idx = tid; idx < Ny * Nx; idx += nth) {
+            const int a = idx / Nx, e = idx % Nx;
+            double s = 0.0;
+            for (int d = 0; d < Nx; ++d) s = fma(Jh[a * Nx + d], Sg[d * Nx + e], s);
+            JS[idx] = s;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < Ny * Ny; idx += nth) {
+        const int a = idx / Ny, b = idx % Ny;
+        double s = (a == b) ? vh[a] : 0.0;
+        if (method_ta) {
+            double t = 0.0;
+            for (int e = 0; e < Nx; ++e) t = fma(JS[a * Nx + e], Jh[b * Nx + e], t);
+            s += t;
+        }
+        cov[((long long)h * Ny + a) * Ny + b] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// a6/a7 analytic NLML gradient, fused with a K rebuild so dK/dtheta is never stored:
+//   dNLL/dtheta = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta)   (R&W eq. 5.9; objective of
+//   optimize.py:322-356).  theta = [ell.., sf, sn] are standard deviations (q1):
+//   dK/dell_d = Kf (x_id-x_jd)^2/ell_d^3,  dK/dsf = 2 Kf/sf,  dK/dsn = 2 sn I.
+//   One CTA per 64x64 lower tile of K^-1; partial sums [tile][Nx+2].
+// ---------------------------------------------------------------------------------------
+template <int NXP>
+__global__ void __launch_bounds__(256)
+nlml_grad_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
+                 const double* __restrict__ hp, const double* __restrict__ Kinv, int ld,
+                 const double* __restrict__ alpha, double* __restrict__ partial)
+{
+    extern __shared__ double sm[];
+    double* Xi = sm; double* Xj = sm + Nx * KB_TILE;
+    __shared__ double red[8][NXP + 2];
+    const int tt = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
+    while (bi * (bi + 1) / 2 > tt) --bi;
+    while ((bi + 1) * (bi + 2) / 2 <= tt) ++bi;
+    const int bj = tt - bi * (bi + 1) / 2;
+    const int i0 = bi * KB_TILE, j0 = bj * KB_TILE;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int idx = tid; idx < Nx * KB_TILE; idx += 256) {
+        const int d = idx / KB_TILE, r = idx % KB_TILE;
+        Xi[idx] = XT[(long long)d * ldx + i0 + r];
+        Xj[idx] = XT[(long long)d * ldx + j0 + r];
+    }
+    __syncthreads();
+    const double sf2 = hp[Nx] * hp[Nx];
+    double g[NXP + 2];
+#pragma unroll
+    for (int d = 0; d < NXP + 2; ++d) g[d] = 0.0;
+    double ie2[NXP];
+#pragma unroll
+    for (int d = 0; d < NXP; ++d) ie2[d] = (d < Nx) ? 1.0 / (hp[d] * hp[d]) : 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = i0 + ty + 16 * r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int col = j0 + tx + 16 * c;
+            if (row >= N || col >= N || col > row) continue;
+            double dist = 0.0, d2[NXP];
+#pragma unroll
+            for (int d = 0; d < NXP; ++d) {
+                d2[d] = 0.0;
+                if (d < Nx) {
+                    const double df = Xi[d * KB_TILE + ty + 16 * r] - Xj[d * KB_TILE + tx + 16 * c];
+                    d2[d] = df * df;
+                    dist = fma(d2[d], ie2[d], dist);
+                }
+            }
+            const double kf = sf2 * exp(-0.5 * dist);
+            const double w = Kinv[(long long)row * ld + col] - alpha[row] * alpha[col];
+            const double mult = (row == col) ? 1.0 : 2.0;
+            const double wk = mult * w * kf;
+#pragma unroll
+            for (int d = 0; d < NXP; ++d) g[d] = fma(wk, d2[d], g[d]);
+            g[NXP] += wk;
+            if (row == col) g[NXP + 1] += w;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < NXP + 2; ++d) g[d] = warp_sum(g[d]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < NXP + 2; ++d) red[tid >> 5][d] = g[d];
+    }
+    __syncthreads();
+    if (tid < Nx + 2) {
+        const int src = (tid < Nx) ? tid : (NXP + (tid - Nx));
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += red[q][src];
+        partial[(long long)tt * (Nx + 2) + tid] = s;
+    }
+}
+
+// deterministic column sums of partial[ntile][m] -> grad[m], with the theta scalings
+__global__ void __launch_bounds__(256)
+nlml_grad_final_kernel(const double* __restrict__ partial, int ntile, int Nx,
+                       const double* __restrict__ hp, double* __restrict__ grad)
+{
+    __shared__ double red[8];
+    const int q = blockIdx.x;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < ntile; t += 256) s += partial[(long long)t * (Nx + 2) + q];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int w = 0; w < 8; ++w) r += red[w];
+        if (q < Nx) r = 0.5 * r / (hp[q] * hp[q] * hp[q]);
+        else if (q == Nx) r = 0.5 * r * 2.0 / hp[Nx];
+        else r = 0.5 * r * 2.0 * hp[Nx + 1];
+        grad[q] = r;
+    }
+}
+
+// extract an N x N block out of a padded slab; mode 0 = as is, 1 = lower triangle with
+// exact zeros above the diagonal (the stored-model convention),
+// 2 = symmetric from the lower triangle
+__global__ void extract_kernel(const double* __restrict__ src, int ld, double* __restrict__ dst, int N, int mode)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= N) return;
+    double v;
+    if (mode == 1) v = (c <= r) ? src[(long long)r * ld + c] : 0.0;
+    else if (mode == 2) v = (c <= r) ? src[(long long)r * ld + c] : src[(long long)c * ld + r];
+    else v = src[(long long)r * ld + c];
+    dst[(long long)r * N + c] = v;
+}

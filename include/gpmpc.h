@@ -1,0 +1,142 @@
+/* gpmpc.h -- C ABI of the B200-native GP regression engine (libgpmpc.so).
+ *
+ * This is the drop-in boundary for the dense Gaussian-process hot path of
+ * helgeanl/GP-MPC.  The reference has no FFI layer of its own (it is pure Python on
+ * numpy/CasADi); the entry points below are what a ctypes binding inside the
+ * reference's gp_mpc/gp_class.py would call instead of numpy/CasADi.  Each entry
+ * point cites the reference code it replaces (file:line relative to the reference
+ * checkout).  See INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Conventions
+ *   - all matrices are fp64, row-major, caller-owned;  "host" pointers are ordinary
+ *     CPU memory, "device" pointers are CUDA device memory on the handle's GPU
+ *   - hyper rows are [ell_1..ell_Nx, sf, sn] with sf, sn STANDARD DEVIATIONS
+ *     (gp_class.py:139-142);  prior mean is zero (the only mean the reference's
+ *     prediction graph ever uses, gp_class.py:69-71)
+ *   - return value: 0 ok, <0 error (gpmpc_last_error(h) has the text),
+ *     GPMPC_ERR_NOTPD when the Cholesky failed even after the jitter retry
+ *   - a handle owns one CUDA stream and is not thread-safe; calls are synchronous
+ *     unless stated otherwise
+ *   - the library has NO CPU fallback: without a CUDA device gpmpc_create fails
+ */
+#ifndef GPMPC_H
+#define GPMPC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpmpc_handle_s* gpmpc_handle_t;
+
+enum {
+    GPMPC_OK = 0,
+    GPMPC_ERR_ARG = -1,
+    GPMPC_ERR_CUDA = -2,
+    GPMPC_ERR_STATE = -3,
+    GPMPC_ERR_NCCL = -4,
+    GPMPC_ERR_NOTPD = -5
+};
+
+/* propagation method of GP.set_method / GP.predict (gp_class.py:193-237) */
+enum { GPMPC_METHOD_ME = 0, GPMPC_METHOD_TA = 1 };
+
+/* selector of gpmpc_get */
+enum {
+    GPMPC_GET_CHOL = 0,    /* (N,N) lower factor, exact zeros above the diagonal (optimize.py:491) */
+    GPMPC_GET_ALPHA = 1,   /* (N,)  K^-1 y                                      (optimize.py:494) */
+    GPMPC_GET_INVK = 2,    /* (N,N) K^-1, symmetric                             (optimize.py:489-490) */
+    GPMPC_GET_K = 3,       /* (N,N) K + sn2 I                                   (optimize.py:480-482) */
+    GPMPC_GET_LOGDET = 4,  /* (1,)  2 sum log L_ii                              (optimize.py:352) */
+    GPMPC_GET_LINV = 5     /* (N,N) L^-1 lower                                  (optimize.py:489 invL) */
+};
+
+/* selector of gpmpc_profile */
+enum {
+    GPMPC_PROF_KBUILD_FULL = 0,   /* covSEard K build, full square                     */
+    GPMPC_PROF_KBUILD_LOWER = 1,  /* covSEard K build, lower triangle only            */
+    GPMPC_PROF_SYRK = 2,          /* Cholesky trailing update C -= P P^T (DMMA GEMM)  */
+    GPMPC_PROF_FACTORIZE = 3,     /* potrf + trtri of one output (K prebuilt each rep) */
+    GPMPC_PROF_TRIGEMM = 4        /* predict v = Linv ks product, all local outputs    */
+};
+
+int gpmpc_version(void);
+
+/* Create an engine for N training points, Nx inputs, Ny outputs of which this handle
+ * owns the contiguous block [out_begin, out_begin+out_count) (one block per GPU rank;
+ * independent per-output GPs, optimize.py:433 / gp_functions.py:128).  device = CUDA
+ * ordinal.  Replaces the array allocations of train_gp_numpy, optimize.py:424-427. */
+int gpmpc_create(int N, int Nx, int Ny, int out_begin, int out_count, int device, gpmpc_handle_t* out);
+int gpmpc_destroy(gpmpc_handle_t h);
+const char* gpmpc_last_error(gpmpc_handle_t h);   /* h may be NULL: last create error */
+
+/* Training data already in the GP's input space (standardised by the caller when
+ * normalize=True, gp_class.py:101-117).  X:(N,Nx) Y:(N,Ny) host. */
+int gpmpc_set_data(gpmpc_handle_t h, const double* X, const double* Y);
+
+/* hyper:(Ny,ld) host, ld >= Nx+2; only the owned rows are used (gp_class.py:134-142). */
+int gpmpc_set_hyper(gpmpc_handle_t h, const double* hyper, int ld);
+
+/* K = covSEard(X,X) + sn2 I for global output a into K_out:(N,N) host (may be NULL:
+ * build only).  Replaces calc_cov_matrix + noise + symmetrise, optimize.py:303-319,
+ * :480-482 and GP.covSEard gp_class.py:314-350. */
+int gpmpc_build_K(gpmpc_handle_t h, int a, double* K_out);
+
+/* Post-fit block for every owned output: K -> L (blocked Cholesky on fp64 tensor
+ * cores) -> L^-1 -> alpha, logdet.  On a non-positive pivot adds `jitter` (reference:
+ * 1e-8) to that output's diagonal ONCE and retries; a second failure returns
+ * GPMPC_ERR_NOTPD.  info:(out_count,) host, may be NULL: 0 ok, 1 = ok after jitter,
+ * >1 = 1 + failing pivot index.  Replaces optimize.py:479-494 (= :267-285,
+ * gp_class.py:516-537). */
+int gpmpc_factorize(gpmpc_handle_t h, double jitter, int* info);
+
+/* Negative log marginal likelihood of global output a at theta:(Nx+2,) host and
+ * (grad != NULL) its analytic gradient:  NLL = 1/2 y^T alpha + 1/2 logdet K (no
+ * N/2 log 2pi term), with the same jitter retry.  Replaces calc_NLL_numpy,
+ * optimize.py:322-356; the gradient replaces SLSQP's finite differences
+ * (optimize.py:466-467).  Invalidates the factorisation of output a. */
+int gpmpc_nlml(gpmpc_handle_t h, int a, const double* theta, double* nll, double* grad);
+
+/* Batched prediction at H test points (host buffers; copies are part of the call).
+ * Z:(H,Nx) in the GP's input space; Sigma:(Nx,Nx) or (H,Nx,Nx) when sigma_per_point
+ * (ignored for ME, may be NULL); outputs (any may be NULL): mean:(H,Ny) var:(H,Ny)
+ * cov:(H,Ny,Ny) jac:(H,Ny,Nx).  With a communicator attached every rank passes the
+ * same Z/Sigma and receives all Ny outputs (one all-gather of H*(2+Nx) doubles per
+ * output).  Replaces build_gp / build_TA_cov evaluation gp_functions.py:111-147,
+ * :167-171 and GP.covar gp_class.py:353-381. */
+int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* Z, const double* Sigma,
+                  int sigma_per_point, double* mean, double* var, double* cov, double* jac);
+
+/* Same with DEVICE pointers, enqueued on the handle's stream; returns without
+ * synchronising unless sync != 0. */
+int gpmpc_predict_device(gpmpc_handle_t h, int method, int H, const double* dZ, const double* dSigma,
+                         int sigma_per_point, double* d_mean, double* d_var, double* d_cov,
+                         double* d_jac, int sync);
+
+/* Copy a result of the last factorisation for global output a into dst (host). */
+int gpmpc_get(gpmpc_handle_t h, int what, int a, double* dst);
+
+/* Engine options: "refine" (0/1: one step of iterative refinement of v = L\ks through
+ * the stored factor), "ksplit" (split-K chunk of the predict product, 0 = auto). */
+int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value);
+
+/* Multi-GPU: one process per GPU.  Rank 0 calls gpmpc_comm_unique_id and ships the
+ * 128 bytes to the other ranks (any transport); every rank then calls
+ * gpmpc_comm_init.  NCCL is loaded with dlopen("libnccl.so.2"). */
+int gpmpc_comm_unique_id(void* id128);
+int gpmpc_comm_init(gpmpc_handle_t h, const void* id128, int rank, int world);
+
+/* The handle's CUDA stream (cudaStream_t) so a caller can record events on it. */
+void* gpmpc_stream(gpmpc_handle_t h);
+int gpmpc_synchronize(gpmpc_handle_t h);
+
+/* Time one kernel of the path with CUDA events on the handle's stream: `reps` launches
+ * after one warm-up, average milliseconds in ms_out[0]; n = problem size override
+ * (0 = the handle's N).  flops/bytes are derived by the caller. */
+int gpmpc_profile(gpmpc_handle_t h, int what, int n, int reps, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPMPC_H */

@@ -77,6 +77,22 @@ def covSEard_expanded(X, Z, ell, sf2):
     return sf2 * np.exp(-.5 * dist)
 
 
+def covSEard_blas(X, Z, ell, sf2):
+    """The expansion form of ``optimize.py:303-319`` with the D per-dimension rank-1
+    updates folded into one BLAS product on the pre-scaled inputs (same arithmetic up to
+    summation order; used where N is too large for D full-size temporaries)."""
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64)) / np.asarray(ell, dtype=np.float64)
+    Z = np.atleast_2d(np.asarray(Z, dtype=np.float64)) / np.asarray(ell, dtype=np.float64)
+    d = -2.0 * (X @ Z.T)
+    d += np.sum(X * X, 1)[:, None]
+    d += np.sum(Z * Z, 1)[None, :]
+    np.maximum(d, 0.0, out=d)
+    d *= -0.5
+    np.exp(d, out=d)
+    d *= sf2
+    return d
+
+
 def calc_cov_matrix(X, ell, sf2):
     """``optimize.py:303-319``: K(X,X) without noise (expansion form)."""
     return covSEard_expanded(X, X, ell, sf2)

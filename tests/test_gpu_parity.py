@@ -1,0 +1,292 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed
+golden fixtures.  Tolerances: mean / covariance 1e-6 batch-inf-norm relative (BASELINE.json
+north_star); chol 2e-9; NLL 1e-9; index work exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+from tests._util import load_fixture, load_golden, relinf
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+
+
+def _engine(N, Nx, Ny, **kw):
+    import gp_mpc_b200
+    return gp_mpc_b200.Engine(N, Nx, Ny, device=0, **kw)
+
+
+def _L():
+    import gp_mpc_b200
+    return gp_mpc_b200._lib
+
+
+def _fit_engine(X, Y, hyper):
+    eng = _engine(X.shape[0], X.shape[1], Y.shape[1])
+    eng.set_data(X, Y)
+    eng.set_hyper(hyper)
+    info = eng.factorize()
+    return eng, info
+
+
+# ------------------------------------------------------------------ a1/a2 K build
+@pytest.mark.parametrize('case', ['tank', 'car', 'syn300', 'syn1000'])
+def test_kbuild_matches_oracle(case):
+    if case in ('tank', 'car'):
+        m = load_fixture(case); X, Y, hyper = m['X'], m['Y'], m['hyper']
+    else:
+        n = int(case[3:]); p = orc.synthetic_problem(n, 7, 2, config_id=n); X, Y, hyper = p['X'], p['Y'], p['hyper']
+    N, Nx = X.shape
+    eng = _engine(N, Nx, Y.shape[1]); eng.set_data(X, Y); eng.set_hyper(hyper)
+    for a in range(Y.shape[1]):
+        K = eng.build_K(a)
+        Ko = orc.covSEard(X, X, hyper[a, :Nx], hyper[a, Nx] ** 2) + hyper[a, Nx + 1] ** 2 * np.eye(N)
+        assert relinf(K, Ko) < 1e-13
+        assert np.array_equal(K, K.T)                     # exactly symmetric (q10)
+        assert relinf(K, orc.assemble_K(X, hyper[a])) < 1e-11   # the reference's expansion form
+    eng.close()
+
+
+# ------------------------------------------------------------------ a3-a5 factorisation
+@pytest.mark.parametrize('name', ['tank', 'car'])
+def test_factorize_reproduces_stored_model(name):
+    m = load_fixture(name)
+    eng, info = _fit_engine(m['X'], m['Y'], m['hyper'])
+    assert not info.any()
+    L = _L()
+    N = m['X'].shape[0]
+    for a in range(m['hyper'].shape[0]):
+        chol = eng.get(L.GET_CHOL, a)
+        assert np.all(np.triu(chol, 1) == 0.0)            # exact zeros above the diagonal
+        assert relinf(chol, m['chol'][a]) < (1e-10 if name == 'tank' else 2e-9)
+        linv = eng.get(L.GET_LINV, a)
+        assert relinf(linv @ chol, np.eye(N)) < 1e-9
+        alpha = eng.get(L.GET_ALPHA, a)
+        # alpha itself is cond(K)*eps limited (1e-9 tank / 1e-5 car, as for the oracle's own rerun)
+        assert relinf(alpha, m['alpha'][a]) < (1e-7 if name == 'tank' else 1e-4)
+        invK = eng.get(L.GET_INVK, a)
+        assert np.array_equal(invK, invK.T)
+        assert relinf(invK, m['invK'][a]) < (1e-7 if name == 'tank' else 1e-4)
+        K = eng.get(L.GET_K, a)
+        assert relinf(chol @ chol.T, K) < 1e-13
+        logdet = eng.get(L.GET_LOGDET, a)[0]
+        assert logdet == pytest.approx(2 * np.sum(np.log(np.diag(m['chol'][a]))), rel=1e-10)
+    eng.close()
+
+
+@pytest.mark.parametrize('N', [129, 384, 1000])
+def test_factorize_synthetic_vs_oracle(N):
+    p = orc.synthetic_problem(N, 8, 3, config_id=N)
+    post = orc.postfit(p['X'], p['Y'], p['hyper'], lapack_general_solve=False)
+    eng, info = _fit_engine(p['X'], p['Y'], p['hyper'])
+    L = _L()
+    for a in range(3):
+        assert relinf(eng.get(L.GET_CHOL, a), post['chol'][a]) < 1e-10
+        assert relinf(eng.get(L.GET_ALPHA, a), post['alpha'][a]) < 1e-7
+    eng.close()
+
+
+def test_jitter_retry_and_not_pd():
+    """optimize.py:483-488: one 1e-8 jitter retry, then LinAlgError."""
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((40, 3)); X[20:] = X[:20]      # exact duplicates -> singular Kf
+    Y = rng.standard_normal((40, 1))
+    hyper = np.array([[1.0, 1.0, 1.0, 1.0, 1e-10]])        # sn2 = 1e-20: K numerically singular
+    eng = _engine(40, 3, 1); eng.set_data(X, Y); eng.set_hyper(hyper)
+    info = eng.factorize(1e-8)
+    assert info[0] == 1                                     # succeeded after jitter
+    Ko = orc.covSEard(X, X, hyper[0, :3], 1.0) + (1e-20 + 1e-8) * np.eye(40)
+    assert relinf(eng.get(_L().GET_CHOL, 0), np.linalg.cholesky(Ko)) < 1e-6
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.factorize(0.0)                                  # retry with zero jitter must fail again
+    eng.close()
+
+
+# ------------------------------------------------------------------ a8-a11 prediction
+@pytest.mark.parametrize('name', ['tank', 'car'])
+def test_predict_fixture_batch(name):
+    m = load_fixture(name); d = load_golden('derived', name)
+    eng, _ = _fit_engine(m['X'], m['Y'], m['hyper'])
+    L = _L()
+    mean, var, cov, jac = eng.predict(d['Zs'], d['Sigma'], L.METHOD_TA)
+    assert relinf(mean, d['mean_b']) < TOL
+    assert relinf(var, d['var_b']) < TOL
+    assert relinf(jac, d['J_b']) < TOL
+    assert relinf(cov, d['cov_b']) < TOL
+    mean2, var2, cov2, _ = eng.predict(d['Zs'], None, L.METHOD_ME, want_jac=False)
+    assert np.array_equal(mean2, mean) and np.array_equal(var2, var)
+    assert relinf(cov2, orc.me_cov(d['var_b'])) < TOL
+    # refinement step must agree as well
+    eng.set_option('refine', 1)
+    mean3, var3, _, _ = eng.predict(d['Zs'], d['Sigma'], L.METHOD_TA)
+    assert relinf(var3, d['var_b']) < TOL and relinf(mean3, d['mean_b']) < TOL
+    eng.close()
+
+
+@pytest.mark.parametrize('N,Nx,Ny,H', [(1000, 8, 6, 30), (300, 5, 2, 70), (130, 10, 3, 1), (2048, 17, 1, 50)])
+def test_predict_synthetic_vs_oracle(N, Nx, Ny, H):
+    p = orc.synthetic_problem(N, Nx, Ny, config_id=N + H, H=H)
+    post = orc.postfit(p['X'], p['Y'], p['hyper'], lapack_general_solve=False)
+    mo, vo = orc.gp_mean_var(p['X'], p['hyper'], post['alpha'], post['chol'], p['Z'])
+    Jo = orc.gp_mean_jac(p['X'], p['hyper'], post['alpha'], p['Z'])
+    co = orc.ta_cov(vo, Jo, p['Sigma'])
+    eng, _ = _fit_engine(p['X'], p['Y'], p['hyper'])
+    mean, var, cov, jac = eng.predict(p['Z'], p['Sigma'], _L().METHOD_TA)
+    assert relinf(mean, mo) < TOL and relinf(var, vo) < TOL and relinf(jac, Jo) < TOL and relinf(cov, co) < TOL
+    assert (var > 0).all()
+    # per-point input covariances (one Sigma per shooting node, mpc_class.py:265-275)
+    Sg = np.stack([p['Sigma'] * (1 + 0.1 * h) for h in range(H)])
+    _, _, cov_pp, _ = eng.predict(p['Z'], Sg, _L().METHOD_TA)
+    assert relinf(cov_pp, orc.ta_cov(vo, Jo, Sg)) < TOL
+    # split-K chunking must not change the result beyond rounding
+    eng.set_option('ksplit', 128)
+    _, var_s, _, _ = eng.predict(p['Z'], p['Sigma'], _L().METHOD_TA)
+    assert relinf(var_s, var) < 1e-9
+    eng.close()
+
+
+def test_full_size_properties_n4096():
+    """C3-size (N=4096) checks that do not need the O(N^3) CPU oracle: L Linv = I on probe
+    columns, the interpolation identity Kf alpha = y - sn2 alpha at training points, var > 0."""
+    N, Nx, Ny = 4096, 8, 2
+    p = orc.synthetic_problem(N, Nx, Ny, config_id=3, H=30)
+    eng, _ = _fit_engine(p['X'], p['Y'], p['hyper'])
+    L = _L()
+    idx = np.arange(0, N, 137)[:30]
+    mean, var, _, _ = eng.predict(p['X'][idx], None, L.METHOD_ME, want_jac=False)
+    for a in range(Ny):
+        alpha = eng.get(L.GET_ALPHA, a)
+        sn2 = p['hyper'][a, Nx + 1] ** 2
+        assert relinf(mean[:, a], p['Y'][idx, a] - sn2 * alpha[idx]) < 1e-7
+    assert (var > 0).all() and (var < 1.0).all()
+    chol = eng.get(L.GET_CHOL, 0); linv = eng.get(L.GET_LINV, 0)
+    probe = np.zeros((N, 4)); probe[[0, 777, 2048, 4095], range(4)] = 1.0
+    assert relinf(chol @ (linv @ probe), probe) < 1e-9
+    K = orc.covSEard(p['X'][:512], p['X'][:512], p['hyper'][0, :Nx], 1.0) + 1e-4 * np.eye(512)
+    assert relinf((chol @ chol.T)[:512, :512], K) < 1e-12
+    eng.close()
+
+
+# ------------------------------------------------------------------ a6/a7 NLML + gradient
+@pytest.mark.parametrize('name', ['tank', 'car'])
+def test_nlml_matches_reference_values(name):
+    m = load_fixture(name); g = load_golden('ref_verbatim', name)
+    eng = _engine(m['X'].shape[0], m['X'].shape[1], m['Y'].shape[1]); eng.set_data(m['X'], m['Y'])
+    for a in range(m['hyper'].shape[0]):
+        nll = eng.nlml(a, m['hyper'][a], grad=False)
+        assert nll == pytest.approx(g['nll'][a], rel=1e-9)
+    eng.close()
+
+
+def test_nlml_gradient_vs_oracle():
+    p = orc.synthetic_problem(200, 4, 2, config_id=11)
+    eng = _engine(200, 4, 2); eng.set_data(p['X'], p['Y'])
+    for a in range(2):
+        th = p['hyper'][a].copy(); th[:4] *= 0.5; th[5] = 5e-3
+        nll, g = eng.nlml(a, th, grad=True)
+        assert nll == pytest.approx(orc.calc_NLL(th, p['X'], p['Y'][:, a]), rel=1e-10)
+        assert relinf(g, orc.calc_NLL_grad_analytic(th, p['X'], p['Y'][:, a])) < 1e-8
+        assert relinf(g, orc.calc_NLL_grad_fd(th, p['X'], p['Y'][:, a])) < 1e-5
+    eng.close()
+
+
+# ------------------------------------------------------------------ the GP class (drop-in boundary)
+def _gp_from_fixture(name):
+    import gp_mpc_b200
+    m = load_fixture(name)
+    kw = dict(mean_func='zero', gp_method='TA', normalize=m['normalize'],
+              hyper=dict(hyper=m['hyper'], invK=m['invK'], alpha=m['alpha'], chol=m['chol'],
+                         length_scale=m['length_scale'], signal_var=m['signal_var'],
+                         noise_var=m['noise_var'], mean=m['mean']))
+    if m['normalize']:
+        kw.update(meta=m['meta'], xlb=m['xlb'], xub=m['xub'], ulb=m['ulb'], uub=m['uub'])
+    return gp_mpc_b200.GP(m['X'], m['Y'], **kw), m
+
+
+@pytest.mark.parametrize('name', ['tank', 'car'])
+def test_gp_class_known_answers(name):
+    gp, m = _gp_from_fixture(name)
+    d = load_golden('derived', name)
+    N, Ny, Nu = gp.get_size()
+    assert (N, Ny, Nu) == (m['X'].shape[0], m['Y'].shape[1], m['X'].shape[1] - m['Y'].shape[1])
+    gp.set_method('TA')
+    mean, cov = gp.predict(d['x0'], d['u0'], d['Sigma'])
+    assert mean.shape == (Ny, 1) and cov.shape == (Ny, Ny)
+    assert relinf(mean, d['mean_ta']) < TOL and relinf(cov, d['cov_ta']) < TOL
+    gp.set_method('ME')
+    mean, cov = gp.predict(d['x0'], d['u0'], d['Sigma'])
+    assert relinf(mean, d['mean_me']) < TOL and relinf(cov, d['cov_me']) < TOL
+    A, B = gp.discrete_linearize(d['x0'], d['u0'], d['Sigma'])
+    assert relinf(A, d['A']) < TOL and relinf(B, d['B']) < TOL
+    with pytest.raises(NameError):
+        gp.set_method('nope')
+    gp.close()
+
+
+def test_gp_class_validate_and_io(tmp_path):
+    gp, m = _gp_from_fixture('tank')
+    rng = np.random.default_rng(1)
+    Xt = m['meta']['meanZ'] + m['meta']['stdZ'] * rng.standard_normal((25, 6)) * 0.5
+    Yt = m['meta']['meanY'] + m['meta']['stdY'] * rng.standard_normal((25, 4)) * 0.5
+    smse, mnlp = gp.validate(Xt, Yt)
+    so, mo = orc.validate(m, Xt, Yt)
+    assert relinf(smse, so) < TOL and relinf(mnlp, mo) < TOL
+    path = str(tmp_path / 'model')
+    gp.save_model(path)
+    with open(path + '.json') as f:
+        dd = json.load(f)
+    assert set(dd) == {'X', 'Y', 'hyper', 'mean_func', 'normalize', 'xlb', 'xub', 'ulb', 'uub', 'meta'}
+    assert set(dd['hyper']) == {'hyper', 'invK', 'alpha', 'chol', 'length_scale', 'signal_var', 'noise_var', 'mean'}
+    assert relinf(np.array(dd['hyper']['chol']), m['chol']) < 1e-10
+    import gp_mpc_b200
+    gp2 = gp_mpc_b200.GP.load_model(path)
+    d = load_golden('derived', 'tank')
+    m1, c1 = gp.predict(d['x0'], d['u0'], d['Sigma'])
+    m2, c2 = gp2.predict(d['x0'], d['u0'], d['Sigma'])
+    assert np.array_equal(m1, m2) and np.array_equal(c1, c2)
+    # batched horizon call == per-point calls
+    xs = np.tile(d['x0'], (5, 1)) * (1 + 0.01 * np.arange(5)[:, None]); us = np.tile(d['u0'], (5, 1))
+    mb, cb = gp.predict_batch(xs, us, d['Sigma'])
+    for h in range(5):
+        mh, ch = gp.predict(xs[h], us[h], d['Sigma'])
+        assert relinf(mb[h], mh.ravel()) < 1e-12 and relinf(cb[h], ch) < 1e-12
+    # kernel helper keeps the reference's error behaviour
+    with pytest.raises(ValueError):
+        gp.covSEard(np.zeros((3, 6)), np.zeros((2, 5)), np.ones(6), 1.0)
+    k = gp.covSEard(m['X'][:5], m['X'][5:9], m['hyper'][0, :6], 2.0)
+    assert relinf(k, orc.covSEard(m['X'][:5], m['X'][5:9], m['hyper'][0, :6], 2.0)) < 1e-13
+    gp.close(); gp2.close()
+
+
+def test_gp_class_trains_like_the_reference_driver():
+    """train_gp_numpy semantics (optimize.py:359-503): same init / bounds / SLSQP; the GPU fit
+    (analytic gradient) must reach an NLL at least as low as the FD-gradient CPU restatement."""
+    import gp_mpc_b200
+    p = orc.synthetic_problem(60, 3, 2, config_id=77)
+    Xr = 3.0 + 2.0 * p['X']; Yr = 1.0 + 0.5 * p['Y']
+    gp = gp_mpc_b200.GP(Xr, Yr, normalize=True, xlb=[0] * 2, xub=[1] * 2, ulb=[0], uub=[1],
+                        optimizer_opts={'maxiter': 300})
+    hy = np.column_stack([gp.get_hyper_parameters()['length_scale'],
+                          np.sqrt(gp.get_hyper_parameters()['signal_var']),
+                          np.sqrt(gp.get_hyper_parameters()['noise_var'])])
+    st = orc.data_stats(Xr, Yr, 2)
+    Xs = (Xr - st['meanZ']) / st['stdZ']; Ys = (Yr - st['meanY']) / st['stdY']
+    ref = orc.train_gp(Xs, Ys, options={'maxiter': 300})
+    for a in range(2):
+        nll_gpu = orc.calc_NLL(hy[a], Xs, Ys[:, a])
+        nll_ref = orc.calc_NLL(ref['hyper'][a], Xs, Ys[:, a])
+        assert nll_gpu <= nll_ref + 1e-3 * abs(nll_ref)
+    # jac='fd' follows the reference's finite-difference trajectory
+    gp_fd = gp_mpc_b200.GP(Xr, Yr, normalize=True, xlb=[0] * 2, xub=[1] * 2, ulb=[0], uub=[1],
+                           optimizer_opts={'maxiter': 300, 'jac': 'fd'})
+    hy_fd = np.column_stack([gp_fd.get_hyper_parameters()['length_scale'],
+                             np.sqrt(gp_fd.get_hyper_parameters()['signal_var']),
+                             np.sqrt(gp_fd.get_hyper_parameters()['noise_var'])])
+    for a in range(2):
+        assert orc.calc_NLL(hy_fd[a], Xs, Ys[:, a]) == pytest.approx(
+            orc.calc_NLL(ref['hyper'][a], Xs, Ys[:, a]), rel=1e-4, abs=1e-3)
+    gp.close(); gp_fd.close()
