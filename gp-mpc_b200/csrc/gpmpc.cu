@@ -180,10 +180,23 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
     return GPMPC_OK;
 }
 
+static int kbuild_configure(gpmpc_handle_t h)
+{
+    static bool conf = false;
+    if (!conf) {
+        CUDA_TRY(cudaFuncSetAttribute(kbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (2 * NX_MAX * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8));
+        conf = true;
+    }
+    return GPMPC_OK;
+}
+
 static int launch_kbuild(gpmpc_handle_t h, const double* dHyp, const double* dJit, double* K, int batch, int full)
 {
     const int T = h->Npad / KB_TILE;
     const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;
+    int rc = kbuild_configure(h);
+    if (rc) return rc;
     dim3 grid(T * (T + 1) / 2, 1, batch);
     kbuild_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, dHyp, h->Nx + 2, dJit,
                                                K, h->Npad, slab(h), full);
@@ -223,6 +236,7 @@ static int factor_one(gpmpc_handle_t h, int a, const double* dHyp, double jitter
         CUDA_TRY(cudaMemcpyAsync(h->dJit + a, &jit, sizeof(double), cudaMemcpyHostToDevice, h->st));
         CUDA_TRY(cudaMemsetAsync(h->dInfo + a, 0, sizeof(int), h->st));
         // kbuild indexes hyper/jitter by blockIdx.z (== 0 here): pass row pointers
+        { int rck = kbuild_configure(h); if (rck) return rck; }
         {
             const int T = h->Npad / KB_TILE;
             const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;
@@ -415,6 +429,8 @@ extern "C" int gpmpc_build_K(gpmpc_handle_t h, int a, double* K_out)
     if (rc) return rc;
     const double zero = 0.0;
     CUDA_TRY(cudaMemcpyAsync(h->dJit + al, &zero, 8, cudaMemcpyHostToDevice, h->st));
+    rc = kbuild_configure(h);
+    if (rc) return rc;
     {
         const int T = h->Npad / KB_TILE;
         const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;

@@ -191,6 +191,8 @@ __global__ void transpose_lower_kernel(const double* __restrict__ Li, double* __
     for (int r = ty; r < 32; r += 8) tile[r][tx] = Li[(long long)(bi * 32 + r) * ld + bj * 32 + tx];
     __syncthreads();
     for (int r = ty; r < 32; r += 8) U[(long long)(bj * 32 + r) * ld + bi * 32 + tx] = tile[tx][r];
+    if (bj < bi)      // keep U exactly upper-triangular (the buffer doubles as a staging area)
+        for (int r = ty; r < 32; r += 8) U[(long long)(bi * 32 + r) * ld + bj * 32 + tx] = 0.0;
 }
 
 // w = T * y with T lower-triangular (one warp per row).   a5: alpha = L^-T (L^-1 y)

@@ -74,7 +74,7 @@ def test_factorize_reproduces_stored_model(name):
         K = eng.get(L.GET_K, a)
         assert relinf(chol @ chol.T, K) < 1e-13
         logdet = eng.get(L.GET_LOGDET, a)[0]
-        assert logdet == pytest.approx(2 * np.sum(np.log(np.diag(m['chol'][a]))), rel=1e-10)
+        assert logdet == pytest.approx(2 * np.sum(np.log(np.diag(m['chol'][a]))), rel=1e-8)
     eng.close()
 
 
