@@ -77,6 +77,10 @@ class ClockSampler:
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+            return
+        t0 = time.time()          # nvidia-smi needs ~0.5 s to emit its first sample
+        while time.time() - t0 < 4.0 and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.05)
 
     def stop(self):
         if self.p is None:
@@ -230,12 +234,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_dev()
     eng.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with torch.cuda.stream(st):

