@@ -32,6 +32,9 @@ struct GemmParams {
     int lower;                       // compute tiles it >= jt only; mask col > row on diagonal tiles
     int ksplit;                      // split-K chunk length (multiple of 16), 0 = off (blockIdx.y = chunk)
     long long sPart;                 // element stride between split-K partial outputs
+    int lpt;                         // longest-processing-time-first block order for k <= j products:
+                                     // grid = (batch, nt reversed, chunk): every output's longest tiles
+                                     // are dispatched first, short partial chunks fill the tail
 };
 
 constexpr int GEMM_BK = 16;
@@ -66,7 +69,14 @@ gemm_dmma_kernel(const GemmParams p)
     const int wm = warp / WN, wn = warp % WN;
 
     int it, jt;
-    if (p.lower) {
+    long long bz = blockIdx.z;
+    int chunk = blockIdx.y;
+    if (p.lpt) {
+        it = 0;
+        jt = p.nt - 1 - (int)blockIdx.y;
+        bz = blockIdx.x;
+        chunk = blockIdx.z;
+    } else if (p.lower) {
         const int tt = blockIdx.x;
         it = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
         while (it * (it + 1) / 2 > tt) --it;
@@ -84,15 +94,14 @@ gemm_dmma_kernel(const GemmParams p)
     if (p.kflags & GEMM_KJ_GE) k_lo = max(k_lo, jt * BN);
     long long part_off = 0;
     if (p.ksplit) {
-        const int cs = blockIdx.y * p.ksplit;
+        const int cs = chunk * p.ksplit;
         k_lo = max(k_lo, cs);
         k_hi = min(k_hi, cs + p.ksplit);
         if (k_lo >= k_hi) return;            // the reducer applies the same chunk-validity rule
-        part_off = (long long)blockIdx.y * p.sPart;
+        part_off = (long long)chunk * p.sPart;
     }
     const int nk = (k_hi - k_lo) / BK;
 
-    const long long bz = blockIdx.z;
     const double* Ag = p.A + bz * p.sA + (long long)it * BM * p.lda;
     const double* Bg = BT ? (p.B + bz * p.sB + (long long)jt * BN * p.ldb)
                           : (p.B + bz * p.sB + (long long)jt * BN);
@@ -200,6 +209,7 @@ static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cuda
     }
     const int tiles = p.lower ? p.mt * (p.mt + 1) / 2 : p.mt * p.nt;
     dim3 grid(tiles, p.ksplit ? nchunks : 1, batch);
+    if (p.lpt) grid = dim3(batch, p.nt, p.ksplit ? nchunks : 1);      // requires mt == 1
     kern<<<grid, WM * WN * 32, SM::BYTES, st>>>(p);
     return cudaGetLastError();
 }

@@ -65,7 +65,7 @@ struct gpmpc_handle_s {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // model
-    double *dXT = nullptr, *dY = nullptr, *dHyp = nullptr, *dJit = nullptr, *dHypTmp = nullptr;
+    double *dXT = nullptr, *dMu = nullptr, *dY = nullptr, *dHyp = nullptr, *dJit = nullptr, *dHypTmp = nullptr;
     double *dL = nullptr, *dLi = nullptr, *dW1 = nullptr, *dW2 = nullptr;
     double *dAlpha = nullptr, *dTmp = nullptr, *dRes = nullptr;
     int* dInfo = nullptr;
@@ -180,26 +180,22 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
     return GPMPC_OK;
 }
 
-static int kbuild_configure(gpmpc_handle_t h)
-{
-    static bool conf = false;
-    if (!conf) {
-        CUDA_TRY(cudaFuncSetAttribute(kbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (2 * NX_MAX * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8));
-        conf = true;
-    }
-    return GPMPC_OK;
-}
-
+// K(theta) for `batch` consecutive outputs: hyper rows at dHyp (stride Nx+2), jitter at dJit,
+// output slabs at K (stride slab).  full = 1 writes the whole square, 0 the lower triangle.
 static int launch_kbuild(gpmpc_handle_t h, const double* dHyp, const double* dJit, double* K, int batch, int full)
 {
-    const int T = h->Npad / KB_TILE;
-    const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;
-    int rc = kbuild_configure(h);
-    if (rc) return rc;
+    static bool conf = false;
+    const int KD = (h->Nx + 3) & ~3, S = ((KD >> 2) & 1) ? KD : KD + 4;
+    const int smem = (2 * KB2_TILE * S + 2 * KB2_TILE + 16) * 8;
+    if (!conf) {
+        CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (2 * KB2_TILE * 36 + 2 * KB2_TILE + 16) * 8));
+        conf = true;
+    }
+    const int T = h->Npad / KB2_TILE;
     dim3 grid(T * (T + 1) / 2, 1, batch);
-    kbuild_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, dHyp, h->Nx + 2, dJit,
-                                               K, h->Npad, slab(h), full);
+    kbuild_dmma_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dMu, dHyp, h->Nx + 2, dJit,
+                                                    K, h->Npad, slab(h), full);
     CUDA_TRY(cudaGetLastError());
     return GPMPC_OK;
 }
@@ -235,15 +231,9 @@ static int factor_one(gpmpc_handle_t h, int a, const double* dHyp, double jitter
         const double jit = attempt ? jitter : 0.0;
         CUDA_TRY(cudaMemcpyAsync(h->dJit + a, &jit, sizeof(double), cudaMemcpyHostToDevice, h->st));
         CUDA_TRY(cudaMemsetAsync(h->dInfo + a, 0, sizeof(int), h->st));
-        // kbuild indexes hyper/jitter by blockIdx.z (== 0 here): pass row pointers
-        { int rck = kbuild_configure(h); if (rck) return rck; }
-        {
-            const int T = h->Npad / KB_TILE;
-            const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;
-            dim3 grid(T * (T + 1) / 2, 1, 1);
-            kbuild_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, dHyp, h->Nx + 2,
-                                                       h->dJit + a, L, h->Npad, slab(h), 0);
-            CUDA_TRY(cudaGetLastError());
+        {   // kbuild indexes hyper/jitter by blockIdx.z (== 0 here): pass row pointers
+            int rck = launch_kbuild(h, dHyp, h->dJit + a, L, 1, 0);
+            if (rck) return rck;
         }
         int rc = potrf_inv_rec(h, L, Li, slab(h), slab(h), h->dInfo + a, 0, h->Npad, 1);
         if (rc) return rc;
@@ -305,6 +295,7 @@ extern "C" int gpmpc_create(int N, int Nx, int Ny, int out_begin, int out_count,
     CUDA_TRY(cudaEventCreate(&h->ev1));
     const long long np = h->Npad;
     ALLOC(h->dXT, (long long)Nx * np);
+    ALLOC(h->dMu, NX_MAX);
     ALLOC(h->dY, (long long)out_count * np);
     ALLOC(h->dHyp, (long long)out_count * (Nx + 2));
     ALLOC(h->dHypTmp, Nx + 2);
@@ -331,7 +322,7 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    double* bufs[] = {h->dXT, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
+    double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
                       h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dG, h->dZ, h->dSigma, h->dMean,
                       h->dVar, h->dJ, h->dCov, h->dU, h->dKinv, h->dGradPart, h->dGrad};
     for (double* b : bufs) if (b) cudaFree(b);
@@ -364,6 +355,13 @@ extern "C" int gpmpc_set_data(gpmpc_handle_t h, const double* X, const double* Y
         for (int d = 0; d < Nx; ++d) xt[(size_t)d * np + i] = X[(size_t)i * Nx + d];
     for (int a = 0; a < h->nloc; ++a)
         for (int i = 0; i < N; ++i) yl[(size_t)a * np + i] = Y[(size_t)i * h->Ny + h->a0 + a];
+    double mu[NX_MAX] = {0.0};              // column means: the K build centres its inputs (translation invariant)
+    for (int d = 0; d < Nx; ++d) {
+        double sacc = 0.0;
+        for (int i = 0; i < N; ++i) sacc += X[(size_t)i * Nx + d];
+        mu[d] = sacc / N;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->dMu, mu, NX_MAX * 8, cudaMemcpyHostToDevice, h->st));
     CUDA_TRY(cudaMemcpyAsync(h->dXT, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, h->st));
     CUDA_TRY(cudaMemcpyAsync(h->dY, yl.data(), yl.size() * 8, cudaMemcpyHostToDevice, h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
@@ -429,16 +427,8 @@ extern "C" int gpmpc_build_K(gpmpc_handle_t h, int a, double* K_out)
     if (rc) return rc;
     const double zero = 0.0;
     CUDA_TRY(cudaMemcpyAsync(h->dJit + al, &zero, 8, cudaMemcpyHostToDevice, h->st));
-    rc = kbuild_configure(h);
+    rc = launch_kbuild(h, h->dHyp + (long long)al * (h->Nx + 2), h->dJit + al, h->dKinv, 1, 1);
     if (rc) return rc;
-    {
-        const int T = h->Npad / KB_TILE;
-        const int smem = (2 * h->Nx * KB_TILE + KB_TILE * (KB_TILE + 1)) * 8;
-        dim3 grid(T * (T + 1) / 2, 1, 1);
-        kbuild_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp + (long long)al * (h->Nx + 2),
-                                                   h->Nx + 2, h->dJit + al, h->dKinv, h->Npad, slab(h), 1);
-        CUDA_TRY(cudaGetLastError());
-    }
     if (K_out) return extract_to_host(h, h->dKinv, K_out, 0);
     CUDA_TRY(cudaStreamSynchronize(h->st));
     return GPMPC_OK;
@@ -622,9 +612,9 @@ static int choose_ksplit(gpmpc_handle_t h)
 {
     const int np = h->Npad, nt = np / 128;
     if (h->opt_ksplit) return h->opt_ksplit >= np ? 0 : std::max(h->opt_ksplit, (np / MAX_CHUNKS + 127) / 128 * 128);
-    long long ks = (long long)h->nloc * nt * nt * 64 / 600;
-    ks = (ks + 127) / 128 * 128;
-    ks = std::max<long long>(ks, 256);
+    // longest-first dispatch bounds the makespan by total/148 + longest item: keep the longest
+    // item (one chunk of k-tiles) at ~10 % of an SM's share, at least 2 k-tiles, at most 16 chunks
+    long long ks = std::max<long long>(2, (long long)h->nloc * nt * nt / 2960) * 128;
     ks = std::max<long long>(ks, (np / MAX_CHUNKS + 127) / 128 * 128);
     return ks >= np ? 0 : (int)ks;
 }
@@ -671,7 +661,7 @@ static int tri_product(gpmpc_handle_t h, const double* Amat, const double* T, in
     p.B = T; p.ldb = np; p.sB = slab(h);
     p.C = h->dPart; p.ldc = np; p.sC = (long long)MAX_CHUNKS * HB * np;
     p.mt = 1; p.nt = np / 128; p.K = np; p.alpha = 1.0; p.beta = 0.0; p.kflags = GEMM_KJ_LE;
-    p.ksplit = ksplit; p.sPart = (long long)HB * np;
+    p.ksplit = ksplit; p.sPart = (long long)HB * np; p.lpt = 1;
     CUDA_TRY(trigemm_launch(bm, p, h->nloc, nch, h->st));
     const int nblk_sq = (np + 255) / 256;
     dim3 g(nblk_sq, Hc, h->nloc);

@@ -93,6 +93,135 @@ kbuild_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
 }
 
 // ---------------------------------------------------------------------------------------
+// a1/a2 (v2)  K build with the pairwise distances on the fp64 TENSOR pipe.
+//   With u_i = sqrt(log2 e) (x_i - mu)/ell and q_i = -1/2 |u_i|^2 + 1/2 log2 sf2,
+//       log2 k(x_i, x_j) = q_i + q_j + u_i . u_j            (= log2 sf2 - log2(e)/2 |xs_i - xs_j|^2)
+//   so the O(N^2 Nx) part is a rank-Nx product done with DMMA m8n8k4 (tensor pipe), leaving the
+//   fp64 pipe only ~14 instructions per pair (two adds, clamp, a 16-entry-table exp2 with a
+//   degree-7 polynomial).  ncu on the v1 kernel showed the fp64 pipe 48 % busy and DRAM 41 %:
+//   the two pipes now overlap and the kernel becomes write-bandwidth bound.
+//   The kernel is translation invariant, so inputs are centred on the column means mu: the
+//   expansion's cancellation error is eps*|u|^2 with |u| measured from the data centre
+//   (<= 6e-16 relative on both reference fixtures, same as direct differences; the reference's
+//   own numpy path uses the un-centred expansion, optimize.py:315-319).
+//   One CTA = one 128x128 tile of the lower triangle; off-diagonal tiles also store the
+//   mirrored tile (each exp2 serves two outputs).  q_i + q_j and the k-ordered dot product are
+//   commutative, so K is bitwise symmetric, including inside diagonal tiles.
+// ---------------------------------------------------------------------------------------
+__constant__ double c_exp2_tab[16] = {
+    1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721,
+    1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951,
+    1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429,
+    1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+
+// 2^t for t <= ~1000; results below 2^-1020 flush to zero.  ~2 ulp.
+__device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ T16)
+{
+    t = fmax(t, -1080.0);
+    const double SH = 6755399441055744.0;            // 1.5 * 2^52: rint(16 t) lands in the low word
+    const double s = fma(t, 16.0, SH);
+    const int n = __double2loint(s);
+    const double f = fma(s - SH, -0.0625, t);        // |f| <= 1/32, exact
+    double p = 1.5252733804059838e-05;               // (ln 2)^k / k!, k = 7..1
+    p = fma(p, f, 0.00015403530393381606);
+    p = fma(p, f, 0.0013333558146428441);
+    p = fma(p, f, 0.009618129107628477);
+    p = fma(p, f, 0.055504108664821576);
+    p = fma(p, f, 0.2402265069591007);
+    p = fma(p, f, 0.6931471805599453);
+    p = fma(p, f, 1.0);
+    p *= T16[n & 15];
+    const int e = n >> 4;
+    if (e < -1020) return 0.0;
+    return __hiloint2double(__double2hiint(p) + (e << 20), __double2loint(p));
+}
+
+#define KB2_TILE 128
+__global__ void __launch_bounds__(256)
+kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const double* __restrict__ mu,
+                   const double* __restrict__ hyp, int hyp_ld, const double* __restrict__ jitter,
+                   double* __restrict__ K, int ld, long long sK, int full)
+{
+    extern __shared__ double sm[];
+    const int KD = (Nx + 3) & ~3;                         // k extent of the MMA, zero padded
+    const int S = ((KD >> 2) & 1) ? KD : KD + 4;          // row stride: S/4 odd => conflict-free frags
+    double* Ui = sm;                                      // [128][S]
+    double* Uj = Ui + KB2_TILE * S;                       // [128][S]
+    double* qi = Uj + KB2_TILE * S;                       // [128]
+    double* qj = qi + KB2_TILE;                           // [128]
+    double* T16 = qj + KB2_TILE;                          // [16]
+
+    const int a = blockIdx.z;
+    const double* hp = hyp + (long long)a * hyp_ld;
+    const int tt = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
+    while (bi * (bi + 1) / 2 > tt) --bi;
+    while ((bi + 1) * (bi + 2) / 2 <= tt) ++bi;
+    const int bj = tt - bi * (bi + 1) / 2;
+    const int i0 = bi * KB2_TILE, j0 = bj * KB2_TILE;
+    const int tid = threadIdx.x;
+    const double sf2 = hp[Nx] * hp[Nx];
+    const double l2sf2 = log2(sf2);
+
+    {   // scaled, centred coordinates of the 128 row points (tid < 128) / column points
+        const int p = (tid < KB2_TILE) ? i0 + tid : j0 + tid - KB2_TILE;
+        double* U = (tid < KB2_TILE) ? Ui + tid * S : Uj + (tid - KB2_TILE) * S;
+        double nrm = 0.0;
+        for (int d = 0; d < S; ++d) {
+            double u = 0.0;
+            if (d < Nx) u = (XT[(long long)d * ldx + p] - mu[d]) * (1.2011224087864498 / hp[d]);
+            U[d] = u;
+            nrm = fma(u, u, nrm);
+        }
+        ((tid < KB2_TILE) ? qi : qj)[tid & (KB2_TILE - 1)] = fma(-0.5, nrm, 0.5 * l2sf2);
+        if (tid < 16) T16[tid] = c_exp2_tab[tid];
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const double dg = hp[Nx + 1] * hp[Nx + 1] + (jitter ? jitter[a] : 0.0);
+    double* Ka = K + (long long)a * sK;
+    const bool offdiag = (bi != bj);
+    const int nk4 = KD >> 2;
+#pragma unroll 1
+    for (int mi = 0; mi < 2; ++mi) {
+        const int rl = warp * 16 + mi * 8 + g;            // local row of this lane's accumulators
+        const int row = i0 + rl;
+        const double* ua = Ui + rl * S + t;
+        const double qr = qi[rl];
+#pragma unroll 1
+        for (int ng = 0; ng < 4; ++ng) {
+            double acc[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+            const double* ub = Uj + (ng * 32 + g) * S + t;
+            for (int kk = 0; kk < nk4; ++kk) {
+                const double av = ua[kk * 4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dmma884(acc[q][0], acc[q][1], av, ub[q * 8 * S + kk * 4]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cl = ng * 32 + q * 8 + 2 * t;
+                const int col = j0 + cl;
+                const double2 qc = *reinterpret_cast<const double2*>(qj + cl);
+                double v0 = exp2_tab(fmin((qr + qc.x) + acc[q][0], l2sf2), T16);
+                double v1 = exp2_tab(fmin((qr + qc.y) + acc[q][1], l2sf2), T16);
+                if (row == col) v0 += dg;
+                if (row == col + 1) v1 += dg;
+                if (row >= N || col >= N) v0 = (row == col) ? 1.0 : 0.0;
+                if (row >= N || col + 1 >= N) v1 = (row == col + 1) ? 1.0 : 0.0;
+                *reinterpret_cast<double2*>(Ka + (long long)row * ld + col) = make_double2(v0, v1);
+                if (full && offdiag) {
+                    Ka[(long long)col * ld + row] = v0;
+                    Ka[(long long)(col + 1) * ld + row] = v1;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // a3 leaf: 128x128 diagonal block  ->  L (in place, zeros above the diagonal) and L^-1.
 //   np.linalg.cholesky at optimize.py:346/485; a non-positive pivot is reported LAPACK
 //   style (1-based global index) so the host can apply the reference's single 1e-8
