@@ -203,6 +203,9 @@ def main():
         raise SystemExit('workload %s has fewer outputs than ranks' % args.workload)
     t0 = time.perf_counter()
     eng = gp_mpc_b200.Engine(N, Nx, Ny, b, n, device=local_rank)
+    for kv in filter(None, os.environ.get('GPMPC_OPTS', '').split(',')):     # e.g. tri_variant=0,gemm_variant=1
+        k, v = kv.split('=')
+        eng.set_option(k, float(v))
     eng.set_data(w['X'], w['Y'])
     eng.set_hyper(w['hyper'])
     if world > 1:

@@ -38,23 +38,24 @@ struct GemmParams {
 };
 
 constexpr int GEMM_BK = 16;
-constexpr int GEMM_STAGES = 4;
 
-template <int BM, int BN, bool BT>
+template <int BM, int BN, bool BT, int STAGES>
 struct GemmSmem {
     static constexpr int LDA_S = GEMM_BK + 4;                 // 160 B rows: (g*32 + t*8) mod 128 distinct
     static constexpr int LDB_S = BT ? (GEMM_BK + 4) : (BN + 4);
     static constexpr int A_STAGE = BM * LDA_S;
     static constexpr int B_STAGE = BT ? BN * LDB_S : GEMM_BK * LDB_S;
-    static constexpr int BYTES = GEMM_STAGES * (A_STAGE + B_STAGE) * 8;
+    static constexpr int BYTES = STAGES * (A_STAGE + B_STAGE) * 8;
 };
 
-template <int BM, int BN, int WM, int WN, bool BT>
-__global__ void __launch_bounds__(WM * WN * 32, 1)
+template <int BM, int BN, int WM, int WN, bool BT, int STAGES, int MINB>
+__global__ void __launch_bounds__(WM * WN * 32, MINB)
 gemm_dmma_kernel(const GemmParams p)
 {
-    using SM = GemmSmem<BM, BN, BT>;
-    constexpr int BK = GEMM_BK, STAGES = GEMM_STAGES, NT = WM * WN * 32;
+    using SM = GemmSmem<BM, BN, BT, STAGES>;
+    constexpr int BK = GEMM_BK, NT = WM * WN * 32;
+    constexpr int RL = BM / BN;                       // lower mode: row tile `it` owns column tiles [0, RL*(it+1))
+    static_assert(BM % BN == 0 || BM < BN, "lower mode needs BM to be a multiple of BN");
     constexpr int LDA_S = SM::LDA_S, LDB_S = SM::LDB_S, A_STAGE = SM::A_STAGE, B_STAGE = SM::B_STAGE;
     constexpr int WTM = BM / WM, WTN = BN / WN, MF = WTM / 8, NF = WTN / 8;
     static_assert(WTM % 8 == 0 && WTN % 8 == 0, "warp tile must be a multiple of the 8x8 MMA");
@@ -78,10 +79,11 @@ gemm_dmma_kernel(const GemmParams p)
         chunk = blockIdx.z;
     } else if (p.lower) {
         const int tt = blockIdx.x;
-        it = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
-        while (it * (it + 1) / 2 > tt) --it;
-        while ((it + 1) * (it + 2) / 2 <= tt) ++it;
-        jt = tt - it * (it + 1) / 2;
+        constexpr int R = RL > 0 ? RL : 1;
+        it = (int)((sqrt(8.0 * (double)tt / R + 1.0) - 1.0) * 0.5);
+        while (R * it * (it + 1) / 2 > tt) --it;
+        while (R * (it + 1) * (it + 2) / 2 <= tt) ++it;
+        jt = tt - R * it * (it + 1) / 2;
     } else {
         it = blockIdx.x / p.nt;
         jt = blockIdx.x - it * p.nt;
@@ -173,7 +175,7 @@ gemm_dmma_kernel(const GemmParams p)
     // epilogue: each lane owns two adjacent columns of every 8x8 fragment -> 16-byte accesses
     double* Cg = p.C + bz * p.sC + part_off;
     const double* Cing = p.Cin ? (p.Cin + bz * p.sCin) : nullptr;
-    const bool diag = p.lower && (it == jt);
+    const bool diag = p.lower && ((jt + 1) * BN > it * BM);      // tile reaches the diagonal
 #pragma unroll
     for (int mi = 0; mi < MF; ++mi) {
         const int row = it * BM + wm * WTM + mi * 8 + g;
@@ -196,18 +198,19 @@ gemm_dmma_kernel(const GemmParams p)
     }
 }
 
-template <int BM, int BN, int WM, int WN, bool BT>
+template <int BM, int BN, int WM, int WN, bool BT, int STAGES, int MINB>
 static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cudaStream_t st)
 {
-    using SM = GemmSmem<BM, BN, BT>;
-    auto kern = gemm_dmma_kernel<BM, BN, WM, WN, BT>;
+    using SM = GemmSmem<BM, BN, BT, STAGES>;
+    auto kern = gemm_dmma_kernel<BM, BN, WM, WN, BT, STAGES, MINB>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int tiles = p.lower ? p.mt * (p.mt + 1) / 2 : p.mt * p.nt;
+    constexpr int R = (BM >= BN) ? BM / BN : 1;
+    const int tiles = p.lower ? R * p.mt * (p.mt + 1) / 2 : p.mt * p.nt;
     dim3 grid(tiles, p.ksplit ? nchunks : 1, batch);
     if (p.lpt) grid = dim3(batch, p.nt, p.ksplit ? nchunks : 1);      // requires mt == 1
     kern<<<grid, WM * WN * 32, SM::BYTES, st>>>(p);

@@ -80,7 +80,7 @@ struct gpmpc_handle_s {
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_ksplit = 0;
+    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 0, opt_tri_variant = 1;
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     char err[512] = "";
@@ -99,10 +99,17 @@ static inline long long wslab(gpmpc_handle_t h) { return (long long)h->Npad * h-
 // ------------------------------------------------------------------------------------
 // GEMM helpers (all operands live in slabs with leading dimension ld)
 // ------------------------------------------------------------------------------------
+// callers describe the problem in 128x128 tiles (mt, nt); variant 1 re-tiles N by 64
 static cudaError_t gemm128(gpmpc_handle_t h, bool bt, const GemmParams& p, int batch)
 {
-    return bt ? gemm_launch<128, 128, 2, 4, true>(p, batch, 1, h->st)
-              : gemm_launch<128, 128, 2, 4, false>(p, batch, 1, h->st);
+    if (h->opt_gemm_variant == 1) {       // 128x64 tiles, 4 warps, 3 stages, 2 CTAs/SM
+        GemmParams q = p;
+        q.nt = p.nt * 2;
+        return bt ? gemm_launch<128, 64, 2, 2, true, 3, 2>(q, batch, 1, h->st)
+                  : gemm_launch<128, 64, 2, 2, false, 3, 2>(q, batch, 1, h->st);
+    }
+    return bt ? gemm_launch<128, 128, 2, 4, true, 4, 1>(p, batch, 1, h->st)
+              : gemm_launch<128, 128, 2, 4, false, 4, 1>(p, batch, 1, h->st);
 }
 
 // Recursive blocked Cholesky + triangular inverse on the diagonal block
@@ -569,6 +576,8 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
         if (v < 0 || v % 128) { set_error(h, "ksplit must be a non-negative multiple of 128"); return GPMPC_ERR_ARG; }
         h->opt_ksplit = v; return GPMPC_OK;
     }
+    if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
+    if (!strcmp(name, "tri_variant")) { h->opt_tri_variant = (int)value; return GPMPC_OK; }
     set_error(h, "unknown option %s", name);
     return GPMPC_ERR_ARG;
 }
@@ -620,22 +629,23 @@ static int choose_ksplit(gpmpc_handle_t h)
 }
 
 template <int BM>
-static cudaError_t trigemm_bm(const GemmParams& p, int batch, int nch, cudaStream_t st)
+static cudaError_t trigemm_bm(int variant, const GemmParams& p, int batch, int nch, cudaStream_t st)
 {
-    return gemm_launch<BM, 128, 1, 8, true>(p, batch, nch, st);
+    if (variant == 1) return gemm_launch<BM, 128, 1, 8, true, 3, 2>(p, batch, nch, st);   // 2 CTAs/SM
+    return gemm_launch<BM, 128, 1, 8, true, 4, 1>(p, batch, nch, st);
 }
 
-static cudaError_t trigemm_launch(int bm, const GemmParams& p, int batch, int nch, cudaStream_t st)
+static cudaError_t trigemm_launch(int variant, int bm, const GemmParams& p, int batch, int nch, cudaStream_t st)
 {
     switch (bm) {
-    case 8: return trigemm_bm<8>(p, batch, nch, st);
-    case 16: return trigemm_bm<16>(p, batch, nch, st);
-    case 24: return trigemm_bm<24>(p, batch, nch, st);
-    case 32: return trigemm_bm<32>(p, batch, nch, st);
-    case 40: return trigemm_bm<40>(p, batch, nch, st);
-    case 48: return trigemm_bm<48>(p, batch, nch, st);
-    case 56: return trigemm_bm<56>(p, batch, nch, st);
-    default: return trigemm_bm<64>(p, batch, nch, st);
+    case 8: return trigemm_bm<8>(variant, p, batch, nch, st);
+    case 16: return trigemm_bm<16>(variant, p, batch, nch, st);
+    case 24: return trigemm_bm<24>(variant, p, batch, nch, st);
+    case 32: return trigemm_bm<32>(variant, p, batch, nch, st);
+    case 40: return trigemm_bm<40>(variant, p, batch, nch, st);
+    case 48: return trigemm_bm<48>(variant, p, batch, nch, st);
+    case 56: return trigemm_bm<56>(variant, p, batch, nch, st);
+    default: return trigemm_bm<64>(variant, p, batch, nch, st);
     }
 }
 
@@ -662,7 +672,7 @@ static int tri_product(gpmpc_handle_t h, const double* Amat, const double* T, in
     p.C = h->dPart; p.ldc = np; p.sC = (long long)MAX_CHUNKS * HB * np;
     p.mt = 1; p.nt = np / 128; p.K = np; p.alpha = 1.0; p.beta = 0.0; p.kflags = GEMM_KJ_LE;
     p.ksplit = ksplit; p.sPart = (long long)HB * np; p.lpt = 1;
-    CUDA_TRY(trigemm_launch(bm, p, h->nloc, nch, h->st));
+    CUDA_TRY(trigemm_launch(h->opt_tri_variant, bm, p, h->nloc, nch, h->st));
     const int nblk_sq = (np + 255) / 256;
     dim3 g(nblk_sq, Hc, h->nloc);
     reduce_sq_kernel<<<g, 256, 0, h->st>>>(h->dPart, np, (long long)HB * np, (long long)MAX_CHUNKS * HB * np, ksplit, np, Hc,

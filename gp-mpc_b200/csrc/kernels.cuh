@@ -182,6 +182,9 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
     const double dg = hp[Nx + 1] * hp[Nx + 1] + (jitter ? jitter[a] : 0.0);
     double* Ka = K + (long long)a * sK;
     const bool offdiag = (bi != bj);
+    const bool mirror = full && offdiag;
+    // tiles that touch the diagonal or the identity tail take the checked epilogue
+    const bool special = !offdiag || (i0 + KB2_TILE > N) || (j0 + KB2_TILE > N);
     const int nk4 = KD >> 2;
 #pragma unroll 1
     for (int mi = 0; mi < 2; ++mi) {
@@ -189,6 +192,8 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
         const int row = i0 + rl;
         const double* ua = Ui + rl * S + t;
         const double qr = qi[rl];
+        double* drow = Ka + (long long)row * ld + j0 + 2 * t;              // direct:  K[row][j0 + cl]
+        double* mcol = Ka + (long long)(j0 + 2 * t) * ld + row;            // mirror:  K[j0 + cl][row]
 #pragma unroll 1
         for (int ng = 0; ng < 4; ++ng) {
             double acc[4][2];
@@ -202,19 +207,22 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int cl = ng * 32 + q * 8 + 2 * t;
-                const int col = j0 + cl;
-                const double2 qc = *reinterpret_cast<const double2*>(qj + cl);
+                const int cl0 = ng * 32 + q * 8;          // + 2t folded into the base pointers
+                const double2 qc = *reinterpret_cast<const double2*>(qj + cl0 + 2 * t);
                 double v0 = exp2_tab(fmin((qr + qc.x) + acc[q][0], l2sf2), T16);
                 double v1 = exp2_tab(fmin((qr + qc.y) + acc[q][1], l2sf2), T16);
-                if (row == col) v0 += dg;
-                if (row == col + 1) v1 += dg;
-                if (row >= N || col >= N) v0 = (row == col) ? 1.0 : 0.0;
-                if (row >= N || col + 1 >= N) v1 = (row == col + 1) ? 1.0 : 0.0;
-                *reinterpret_cast<double2*>(Ka + (long long)row * ld + col) = make_double2(v0, v1);
-                if (full && offdiag) {
-                    Ka[(long long)col * ld + row] = v0;
-                    Ka[(long long)(col + 1) * ld + row] = v1;
+                if (special) {
+                    const int col = j0 + cl0 + 2 * t;
+                    if (row == col) v0 += dg;
+                    if (row == col + 1) v1 += dg;
+                    if (row >= N || col >= N) v0 = (row == col) ? 1.0 : 0.0;
+                    if (row >= N || col + 1 >= N) v1 = (row == col + 1) ? 1.0 : 0.0;
+                }
+                *reinterpret_cast<double2*>(drow + cl0) = make_double2(v0, v1);
+                if (mirror) {
+                    double* m = mcol + (long long)cl0 * ld;
+                    m[0] = v0;
+                    m[ld] = v1;
                 }
             }
         }
