@@ -80,7 +80,7 @@ struct gpmpc_handle_s {
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 0, opt_tri_variant = 1;
+    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 1, opt_tri_variant = 1;
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     char err[512] = "";
