@@ -296,10 +296,17 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    traffic = None
+    try:      # per-launch DRAM bytes from the committed ncu capture (profiles/), same workload only
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+        if N == 16384 and H == 50:
+            traffic = n * tj['trigemm_N16384_H50_per_output_bytes']
+    except Exception:
+        pass
     roofline = {'bound': 'tensor', 'kernel': 'gemm_dmma_kernel<BM,128,1,8,NT> (v = Linv ks, split-K)',
                 'achieved': achieved, 'peak': dgemm_tf, 'unit': 'TFLOP/s', 'frac': achieved / dgemm_tf,
                 'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (fp64 is absent from MEASURED_PEAKS.json)',
-                'ms_per_launch': ms_tri, 'traffic': None,
+                'ms_per_launch': ms_tri, 'traffic': traffic, 'algorithmic_bytes': n * 4.0 * N * N,
                 'hbm_view': {'algorithmic_gbs': n * 4.0 * N * N / (ms_tri * 1e-3) / 1e9, 'peak_gbs': hbm_peak,
                              'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}}
 

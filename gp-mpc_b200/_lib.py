@@ -34,6 +34,7 @@ SYMBOLS = [
     ('gpmpc_factorize', C.c_int, [_H, C.c_double, _ip]),
     ('gpmpc_nlml', C.c_int, [_H, C.c_int, _dp, _dp, _dp]),
     ('gpmpc_predict', C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]),
+    ('gpmpc_posterior_cov', C.c_int, [_H, C.c_int, _dp, _dp]),
     ('gpmpc_predict_device', C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ('gpmpc_get', C.c_int, [_H, C.c_int, C.c_int, _dp]),
@@ -183,6 +184,13 @@ class Engine:
         self._check(self.lib.gpmpc_predict(self.h, int(method), H, _ptr(Z), _ptr(Sigma), spp,
                                            _ptr(mean), _ptr(var), _ptr(cov), _ptr(jac)))
         return mean, var, cov, jac
+
+    def posterior_cov(self, Z):
+        """(out_count, H, H): sf2 - V^T V per owned output (GP.covar)."""
+        Z = _f64(Z).reshape(-1, self.Nx)
+        out = np.empty((self.out_count, Z.shape[0], Z.shape[0]))
+        self._check(self.lib.gpmpc_posterior_cov(self.h, Z.shape[0], _ptr(Z), _ptr(out)))
+        return out
 
     def predict_device(self, method, H, dZ, dSigma, spp, d_mean, d_var, d_cov, d_jac, sync=False):
         """Raw device-pointer variant (ints); enqueues on the handle's stream."""

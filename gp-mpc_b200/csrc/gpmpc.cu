@@ -802,6 +802,46 @@ extern "C" int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* 
     return GPMPC_OK;
 }
 
+extern "C" int gpmpc_posterior_cov(gpmpc_handle_t h, int H, const double* Z, double* out)
+{
+    if (!h || !Z || !out || H < 1) return GPMPC_ERR_ARG;
+    if (!h->factorized) { set_error(h, "gpmpc_posterior_cov: call gpmpc_factorize first"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_predict_bufs(h, H);
+    if (rc) return rc;
+    const int np = h->Npad, Nx = h->Nx, nl = h->nloc;
+    const long long sVall = (long long)H * np;            // all H solved rows of one output
+    double *dVall = nullptr, *dOut = nullptr;
+    ALLOC(dVall, (long long)nl * sVall);
+    ALLOC(dOut, (long long)nl * H * H);
+    if (!h->dV) { ALLOC(h->dV, (long long)nl * HB * np); ALLOC(h->dR, (long long)nl * HB * np); }
+    CUDA_TRY(cudaMemcpyAsync(h->dZ, Z, (size_t)H * Nx * 8, cudaMemcpyHostToDevice, h->st));
+    const int ksplit = choose_ksplit(h);
+    const int nblk_mj = (np + KS_CHUNK - 1) / KS_CHUNK;
+    for (int h0 = 0; h0 < H && rc == GPMPC_OK; h0 += HB) {
+        const int Hc = std::min(HB, H - h0), bm = (Hc + 7) / 8 * 8;
+        const double* dZc = h->dZ + (long long)h0 * Nx;
+        cudaError_t e = (Nx <= 8) ? launch_ks<8>(h, dZc, Hc, bm, nblk_mj)
+                      : (Nx <= 16) ? launch_ks<16>(h, dZc, Hc, bm, nblk_mj) : launch_ks<32>(h, dZc, Hc, bm, nblk_mj);
+        if (e != cudaSuccess) { set_error(h, "posterior_cov ks: %s", cudaGetErrorString(e)); rc = GPMPC_ERR_CUDA; break; }
+        rc = tri_product(h, h->dKST, h->dLi, bm, Hc, ksplit, h->dV);
+        if (rc) break;
+        dim3 g(1, Hc, nl);
+        copy2d_kernel<<<dim3(16, std::min(Hc, 64), nl), 128, 0, h->st>>>(h->dV, np, (long long)HB * np,
+                                                                     dVall + (long long)h0 * np, np, sVall, Hc, np);
+        if (cudaGetLastError() != cudaSuccess) { rc = GPMPC_ERR_CUDA; break; }
+    }
+    if (rc == GPMPC_OK) {
+        gram_cov_kernel<<<dim3(H, H, nl), 256, 0, h->st>>>(dVall, np, sVall, np, h->dHyp, Nx + 2, Nx, H, dOut);
+        if (cudaGetLastError() != cudaSuccess) rc = GPMPC_ERR_CUDA;
+    }
+    if (rc == GPMPC_OK && cudaMemcpyAsync(out, dOut, (size_t)nl * H * H * 8, cudaMemcpyDeviceToHost, h->st) != cudaSuccess) rc = GPMPC_ERR_CUDA;
+    cudaStreamSynchronize(h->st);
+    cudaFree(dVall); cudaFree(dOut);
+    if (rc == GPMPC_ERR_CUDA) set_error(h, "gpmpc_posterior_cov: CUDA failure %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------
 // multi-GPU
 // ------------------------------------------------------------------------------------

@@ -693,3 +693,29 @@ __global__ void extract_kernel(const double* __restrict__ src, int ld, double* _
     else v = src[(long long)r * ld + c];
     dst[(long long)r * N + c] = v;
 }
+
+// Gram matrix of the solved columns: out[a][h1][h2] = sf2_a - sum_i V[a][h1][i] V[a][h2][i]
+// (GP.covar, gp_class.py:380: kss - v.T @ v with the scalar kss).  grid (H, H, outputs).
+__global__ void __launch_bounds__(256)
+gram_cov_kernel(const double* __restrict__ V, int ldv, long long sV, int n,
+                const double* __restrict__ hyp, int hyp_ld, int Nx, int H, double* __restrict__ out)
+{
+    __shared__ double red[8];
+    const int a = blockIdx.z, h1 = blockIdx.y, h2 = blockIdx.x;
+    if (h2 > h1) return;                                   // symmetric: lower half computed, both written
+    const double* v1 = V + (long long)a * sV + (long long)h1 * ldv;
+    const double* v2 = V + (long long)a * sV + (long long)h2 * ldv;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s = fma(v1[i], v2[i], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int q = 0; q < 8; ++q) r += red[q];
+        const double sf = hyp[(long long)a * hyp_ld + Nx];
+        const double c = sf * sf - r;
+        out[((long long)a * H + h1) * H + h2] = c;
+        out[((long long)a * H + h2) * H + h1] = c;
+    }
+}

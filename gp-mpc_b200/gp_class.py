@@ -335,6 +335,29 @@ class GP:
             eng.close()
         return K[:n1, n1:].copy()
 
+    def covar(self, X_new):
+        """ Compute covariance of input data  (reference gp_class.py:353-381)
+
+        # Arguments:
+            X_new: Input matrix or vector of size (n x D), in the GP's (standardised) space.
+        # Returns:
+            covar: (D x (n x n)) -- the reference allocates D = input-dimension slabs and fills
+                   the first Ny with  kss - v^T v  (q12); (D x n) for a 1-D input.
+        """
+        X_new = np.asarray(X_new, dtype=np.float64)
+        one_d = X_new.ndim == 1
+        Z = X_new.reshape(1, -1) if one_d else X_new
+        n, D = Z.shape
+        eng = self.__engine
+        mine = [(eng.out_begin, eng.posterior_cov(Z))]
+        if self.__comm.world > 1 and self.__mode == 'outputs':
+            mine = self.__comm.allgather_object(mine[0])
+        covar = np.zeros((D, n) if one_d else (D, n, n))
+        for b, blk in mine:
+            for k in range(blk.shape[0]):
+                covar[b + k] = blk[k].reshape(n) if one_d else blk[k]
+        return covar
+
     def update_data_all(self, X_new, Y_new):
         """ Update training data with all new observations  (reference gp_class.py:474-550):
         append, keep the hyper-parameters, rebuild chol / alpha on the GPU. """

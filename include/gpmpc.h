@@ -108,6 +108,12 @@ int gpmpc_nlml(gpmpc_handle_t h, int a, const double* theta, double* nll, double
 int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* Z, const double* Sigma,
                   int sigma_per_point, double* mean, double* var, double* cov, double* jac);
 
+/* Full posterior covariance between H test points for every OWNED output:
+ * out:(out_count,H,H) host, out[a] = sf2_a - V_a^T V_a with V_a = L_a \ k(X, Z)  (the scalar
+ * kss = sf2 is broadcast over the whole matrix exactly as the reference does).  Replaces
+ * GP.covar, gp_class.py:353-381. */
+int gpmpc_posterior_cov(gpmpc_handle_t h, int H, const double* Z, double* out);
+
 /* Same with DEVICE pointers, enqueued on the handle's stream; returns without
  * synchronising unless sync != 0. */
 int gpmpc_predict_device(gpmpc_handle_t h, int method, int H, const double* dZ, const double* dSigma,

@@ -171,6 +171,44 @@ def test_full_size_properties_n4096():
     eng.close()
 
 
+def test_full_size_properties_n16384():
+    """BASELINE.json's full size (C5: N=16384, Nx=10, H=50), one output: oracle-free
+    properties.  (1) interpolation identity  Kf alpha = y - sn2 alpha  read off the predicted
+    mean at training points; (2) var in (0, sf2); (3) L L^-1 = I on probe columns;
+    (4) L L^T reproduces K on a 512 block; (5) TA covariance is symmetric PSD-plus-diagonal and
+    reduces to ME when Sigma = 0; (6) refinement and split-K variants agree."""
+    N, Nx, H = 16384, 10, 50
+    p = orc.synthetic_problem(N, Nx, 1, config_id=5, H=H)
+    eng, info = _fit_engine(p['X'], p['Y'], p['hyper'])
+    assert not info.any()
+    L = _L()
+    idx = np.arange(0, N, 331)[:H]
+    mean, var, _, _ = eng.predict(p['X'][idx], None, L.METHOD_ME, want_jac=False)
+    alpha = eng.get(L.GET_ALPHA, 0)
+    sn2 = p['hyper'][0, Nx + 1] ** 2
+    assert relinf(mean[:, 0], p['Y'][idx, 0] - sn2 * alpha[idx]) < 1e-6
+    assert (var > 0).all() and (var < 1.0).all()
+    chol = eng.get(L.GET_CHOL, 0)
+    assert np.all(chol[0, 1:] == 0.0) and np.all(np.diag(chol) > 0)
+    Kb = orc.covSEard(p['X'][:512], p['X'][:512], p['hyper'][0, :Nx], 1.0) + sn2 * np.eye(512)
+    assert relinf(chol[:512, :512] @ chol[:512, :512].T, Kb) < 1e-12
+    linv = eng.get(L.GET_LINV, 0)
+    probe = np.zeros((N, 3)); probe[[5, 8191, 16383], range(3)] = 1.0
+    assert relinf(chol @ (linv @ probe), probe) < 1e-8
+    del chol, linv
+    mean_t, var_t, cov_t, jac_t = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
+    _, _, cov_0, _ = eng.predict(p['Z'], np.zeros((Nx, Nx)), L.METHOD_TA)
+    assert np.array_equal(cov_0[:, 0, 0], var_t[:, 0])
+    assert relinf(cov_t[:, 0, 0], var_t[:, 0] + np.einsum('hd,de,he->h', jac_t[:, 0], p['Sigma'], jac_t[:, 0])) < 1e-12
+    eng.set_option('refine', 1)
+    _, var_r, _, _ = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
+    assert relinf(var_r, var_t) < 1e-6
+    eng.set_option('refine', 0); eng.set_option('ksplit', 4096)
+    _, var_k, _, _ = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
+    assert relinf(var_k, var_t) < 1e-8
+    eng.close()
+
+
 # ------------------------------------------------------------------ a6/a7 NLML + gradient
 @pytest.mark.parametrize('name', ['tank', 'car'])
 def test_nlml_matches_reference_values(name):
@@ -259,6 +297,12 @@ def test_gp_class_validate_and_io(tmp_path):
     # kernel helper keeps the reference's error behaviour
     with pytest.raises(ValueError):
         gp.covSEard(np.zeros((3, 6)), np.zeros((2, 5)), np.ones(6), 1.0)
+    # GP.covar: full posterior covariance between test points, odd (D,n,n) shape kept (q12)
+    g = load_golden('ref_verbatim', 'tank')
+    cv = gp.covar(g['Zt'])
+    assert cv.shape == g['covar'].shape and np.all(cv[4:] == 0.0)
+    for a in range(4):
+        assert relinf(cv[a], g['covar'][a]) < TOL            # vs the reference's own GP.covar output
     k = gp.covSEard(m['X'][:5], m['X'][5:9], m['hyper'][0, :6], 2.0)
     assert relinf(k, orc.covSEard(m['X'][:5], m['X'][5:9], m['hyper'][0, :6], 2.0)) < 1e-13
     gp.close(); gp2.close()
