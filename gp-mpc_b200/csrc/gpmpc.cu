@@ -80,7 +80,7 @@ struct gpmpc_handle_s {
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 1, opt_tri_variant = 1;
+    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 1, opt_tri_variant = 1, opt_leaf_variant = 1;
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     char err[512] = "";
@@ -126,13 +126,17 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
     const int ld = h->Npad;
     if (n <= LEAF_N) {
         static bool conf = false;
-        const int smem = LEAF_N * LEAF_LD * 8;
         if (!conf) {
-            CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_N * LEAF_LD * 8));
+            CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_DOUBLES * 8));
             conf = true;
         }
-        leaf_potrf_trtri_kernel<<<batch, 256, smem, h->st>>>(A + (long long)off * ld + off, ld, sA,
-                                                              Li + (long long)off * ld + off, ld, sLi, dInfo, off);
+        if (h->opt_leaf_variant == 0)
+            leaf_potrf_trtri_kernel<<<batch, 256, LEAF_N * LEAF_LD * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
+                                                                              Li + (long long)off * ld + off, ld, sLi, dInfo, off);
+        else
+            leaf_potrf_trtri_v2_kernel<<<batch, 256, LF_SMEM_DOUBLES * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
+                                                                                Li + (long long)off * ld + off, ld, sLi, dInfo, off);
         CUDA_TRY(cudaGetLastError());
         return GPMPC_OK;
     }
@@ -578,6 +582,7 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
     }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "tri_variant")) { h->opt_tri_variant = (int)value; return GPMPC_OK; }
+    if (!strcmp(name, "leaf_variant")) { h->opt_leaf_variant = (int)value; return GPMPC_OK; }
     set_error(h, "unknown option %s", name);
     return GPMPC_ERR_ARG;
 }

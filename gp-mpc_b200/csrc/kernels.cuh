@@ -304,6 +304,179 @@ leaf_potrf_trtri_kernel(double* __restrict__ A, int lda, long long sA,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// a3 leaf v2: blocked (nb = 16) Cholesky + triangular inverse of a 128x128 diagonal block,
+// entirely in shared memory.  Per block step: one warp factorises and inverts the 16x16
+// diagonal block (smem, __syncwarp only); all threads form the panel L21 = A21 D^-T with the
+// small inverse; the trailing update and the inverse assembly run on DMMA fragments read
+// straight from shared memory (row stride 132 doubles: (g*32 + t*8) mod 128 conflict-free).
+// Same outputs / info convention as the v1 kernel (which it replaced: 233 us -> see profiles/).
+// ---------------------------------------------------------------------------------------
+#define LF_LD 132
+#define LF_NB 16
+#define LF_XLD 20
+#define LF_SMEM_DOUBLES (LEAF_N * LF_LD + 8 * 16 * 17 + 2 * LEAF_N * LF_XLD)
+
+__device__ __forceinline__ void warp_potrf16_trtri16(double* D, double* Dinv, int* info, int info_val0, int lane)
+{
+    // D: 16x16 block (lower part valid) with row stride LF_LD; Dinv: [16][17]
+    const int r = lane & 15, hf = lane >> 4;
+    for (int j = 0; j < 16; ++j) {
+        const double d = D[j * LF_LD + j];
+        if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, info_val0 + j + 1);
+        const double pv = sqrt(d), ip = 1.0 / pv;
+        __syncwarp();
+        if (lane == j) D[j * LF_LD + j] = pv;
+        else if (lane > j && lane < 16) D[lane * LF_LD + j] *= ip;
+        __syncwarp();
+        if (r > j) {
+            const double lrj = D[r * LF_LD + j];
+            for (int k = j + 1 + hf; k <= r; k += 2) D[r * LF_LD + k] = fma(-lrj, D[k * LF_LD + j], D[r * LF_LD + k]);
+        }
+        __syncwarp();
+    }
+    if (lane < 16) {       // column `lane` of the inverse by forward substitution, x kept in registers
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) sacc = fma(D[i * LF_LD + k], x[k], sacc);
+            const double idg = 1.0 / D[i * LF_LD + i];
+            x[i] = (i < lane) ? 0.0 : ((i == lane) ? idg : -sacc * idg);
+            Dinv[i * 17 + lane] = x[i];
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(256, 1)
+leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
+                           double* __restrict__ Li, int ldi, long long sLi,
+                           int* __restrict__ info, int info_base)
+{
+    extern __shared__ __align__(16) double S[];                // [128][132]
+    double* DinvAll = S + LEAF_N * LF_LD;                      // [8][16][17]
+    double* Xs = DinvAll + 8 * 16 * 17;                        // [128][20]
+    double* Ys = Xs + LEAF_N * LF_XLD;                         // [128][20]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    double* Ab = A + (long long)blockIdx.x * sA;
+    double* Lb = Li + (long long)blockIdx.x * sLi;
+    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
+        const int r = idx >> 7, c = idx & 127;
+        S[r * LF_LD + c] = Ab[(long long)r * lda + c];
+    }
+    __syncthreads();
+
+    // ---------------- Cholesky, right-looking, nb = 16 ----------------
+    for (int kb = 0; kb < 8; ++kb) {
+        const int c0 = kb * LF_NB;
+        double* Dinv = DinvAll + kb * 16 * 17;
+        if (warp == 0) warp_potrf16_trtri16(S + c0 * LF_LD + c0, Dinv, info + blockIdx.x, info_base + c0, lane);
+        __syncthreads();
+        const int nbel = LEAF_N - c0 - LF_NB;                  // rows below the diagonal block
+        {   // panel: P[r][j] = sum_{k<=j} A[r][c0+k] * Dinv[j][k]; two threads per row (8 columns each)
+            const int rr = tid >> 1, half = tid & 1;
+            double a[16];
+            if (rr < nbel) {
+                const double* src = S + (c0 + LF_NB + rr) * LF_LD + c0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) a[k] = src[k];
+            }
+            __syncwarp();
+            if (rr < nbel) {
+                double* dst = S + (c0 + LF_NB + rr) * LF_LD + c0;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = half * 8 + jj;
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) if (k <= j) sacc = fma(a[k], Dinv[j * 17 + k], sacc);
+                    dst[j] = sacc;
+                }
+            }
+        }
+        __syncthreads();
+        {   // trailing update on 8x8 tiles of the lower triangle: C -= P_R P_C^T  (DMMA)
+            const int nt8 = nbel >> 3;
+            const int ntile = nt8 * (nt8 + 1) / 2;
+            for (int tl = warp; tl < ntile; tl += 8) {
+                int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+                while (ti * (ti + 1) / 2 > tl) --ti;
+                while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+                const int tj = tl - ti * (ti + 1) / 2;
+                const int R0 = c0 + LF_NB + 8 * ti, C0 = c0 + LF_NB + 8 * tj;
+                double* cp = S + (R0 + g) * LF_LD + C0 + 2 * t;
+                double acc0 = cp[0], acc1 = cp[1];
+                const double* pa = S + (R0 + g) * LF_LD + c0 + t;
+                const double* pb = S + (C0 + g) * LF_LD + c0 + t;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) dmma884(acc0, acc1, -pa[kk * 4], pb[kk * 4]);
+                cp[0] = acc0; cp[1] = acc1;
+            }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
+        const int r = idx >> 7, c = idx & 127;
+        Ab[(long long)r * lda + c] = (c <= r) ? S[r * LF_LD + c] : 0.0;
+    }
+    __syncthreads();
+
+    // ---------------- triangular inverse, block column by block column, last first ----------------
+    for (int jb = 7; jb >= 0; --jb) {
+        const int c0 = jb * LF_NB;
+        const int nbel = LEAF_N - c0 - LF_NB;
+        const double* Dinv = DinvAll + jb * 16 * 17;
+        const int b0 = c0 + LF_NB;                             // first row/col of the trailing block
+        // X = L[below, c0:c0+16]
+        for (int idx = tid; idx < nbel * 16; idx += 256) Xs[(idx >> 4) * LF_XLD + (idx & 15)] = S[(b0 + (idx >> 4)) * LF_LD + c0 + (idx & 15)];
+        __syncthreads();
+        // Y = T X with T = Linv[below, below] (lower): row tile i0 uses k in [0, i0+8)
+        for (int rt = warp; rt < (nbel >> 3); rt += 8) {
+            const int i0 = rt * 8;
+            double y00 = 0.0, y01 = 0.0, y10 = 0.0, y11 = 0.0;
+            const double* ta = S + (b0 + i0 + g) * LF_LD + b0 + t;
+            for (int k0 = 0; k0 < i0 + 8; k0 += 4) {
+                const double av = ta[k0];
+                const double* xb = Xs + (k0 + t) * LF_XLD + g;
+                dmma884(y00, y01, av, xb[0]);
+                dmma884(y10, y11, av, xb[8]);
+            }
+            double* yp = Ys + (i0 + g) * LF_XLD + 2 * t;
+            yp[0] = y00; yp[1] = y01; yp[8] = y10; yp[9] = y11;
+        }
+        __syncthreads();
+        {   // Linv[below, c0+j] = - sum_{k>=j} Y[.,k] Dinv[k][j]; two threads per row
+            const int rr = tid >> 1, half = tid & 1;
+            if (rr < nbel) {
+                double yv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) yv[k] = Ys[rr * LF_XLD + k];
+                double* dst = S + (b0 + rr) * LF_LD + c0;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = half * 8 + jj;
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) if (k >= j) sacc = fma(yv[k], Dinv[k * 17 + j], sacc);
+                    dst[j] = -sacc;
+                }
+            }
+        }
+        // diagonal block of the inverse (exact zeros above its diagonal: later DMMA k-ranges read them)
+        if (tid < 256) {
+            const int r = tid >> 4, c = tid & 15;
+            S[(c0 + r) * LF_LD + c0 + c] = (c <= r) ? Dinv[r * 17 + c] : 0.0;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
+        const int r = idx >> 7, c = idx & 127;
+        Lb[(long long)r * ldi + c] = (c <= r) ? S[r * LF_LD + c] : 0.0;
+    }
+}
+
 // batched 2-D copy  dst[b][r][c] = src[b][r][c]   (cols multiple of 2, 16-byte aligned)
 __global__ void copy2d_kernel(const double* __restrict__ src, int lds, long long ss,
                               double* __restrict__ dst, int ldd, long long sd, int rows, int cols)
