@@ -212,6 +212,10 @@ def main():
         box = [eng.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         eng.comm_init(box[0], rank, world)
+        if os.environ.get('GPMPC_NO_PEER', '0') != '1':     # fused epilogue + all-gather over peer memory
+            hs = [None] * world
+            dist.all_gather_object(hs, eng.peer_export(max(64, H)))
+            eng.peer_attach(hs)
     eng.factorize()
     t_setup = time.perf_counter() - t0
 
@@ -335,7 +339,9 @@ def main():
                 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': wl['name'], 'method': 'TA', 'N': N, 'Nx': Nx, 'Ny': Ny, 'H': H,
-                           'parallelism': 'outputs sharded %d/GPU, NCCL all-gather' % n,
+                           'parallelism': 'outputs sharded %d/GPU, %s' % (n, 'single GPU' if world == 1 else (
+                               'NCCL all-gather' if os.environ.get('GPMPC_NO_PEER', '0') == '1' else
+                               'epilogue stores to NVLink peer buffers (fused all-gather), NCCL fallback')),
                            'l2': 'flush 256MB between steps' if flush else 'model %.1f GB/rank > L2, no flush' % (model_bytes / 1e9),
                            'setup_s': t_setup},
                 'clocks': clocks,

@@ -41,6 +41,8 @@ SYMBOLS = [
     ('gpmpc_set_option', C.c_int, [_H, C.c_char_p, C.c_double]),
     ('gpmpc_comm_unique_id', C.c_int, [C.c_void_p]),
     ('gpmpc_comm_init', C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
+    ('gpmpc_peer_export', C.c_int, [_H, C.c_int, C.c_void_p]),
+    ('gpmpc_peer_attach', C.c_int, [_H, C.c_void_p]),
     ('gpmpc_stream', C.c_void_p, [_H]),
     ('gpmpc_synchronize', C.c_int, [_H]),
     ('gpmpc_profile', C.c_int, [_H, C.c_int, C.c_int, C.c_int, _dp]),
@@ -210,6 +212,16 @@ class Engine:
     def comm_init(self, uid, rank, world):
         buf = C.create_string_buffer(bytes(uid), 128)
         self._check(self.lib.gpmpc_comm_init(self.h, buf, int(rank), int(world)))
+
+    def peer_export(self, Hcap=256):
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.gpmpc_peer_export(self.h, int(Hcap), buf))
+        return bytes(buf.raw)
+
+    def peer_attach(self, handles):
+        blob = b''.join(bytes(x) for x in handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self.lib.gpmpc_peer_attach(self.h, buf))
 
     def stream(self):
         return self.lib.gpmpc_stream(self.h)

@@ -83,6 +83,11 @@ struct gpmpc_handle_s {
     int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 1, opt_tri_variant = 1, opt_leaf_variant = 1;
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
+    // peer (CUDA IPC) exchange: [flags: 2*MAXW u64][gather buffer parity 0][parity 1]
+    double* dPeerBlock = nullptr; long long peerGsz = 0; int peerHcap = 0; bool peer_ready = false;
+    double* peerBase[GPMPC_MAXW] = {nullptr}; bool peerOpened[GPMPC_MAXW] = {false};
+    unsigned int* dPeerCounter = nullptr; int* dPeerStatus = nullptr;
+    unsigned long long peer_step = 0; int opt_peer = 1;
     char err[512] = "";
 };
 
@@ -333,6 +338,10 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int r = 0; r < GPMPC_MAXW; ++r) if (h->peerOpened[r]) cudaIpcCloseMemHandle(h->peerBase[r]);
+    if (h->dPeerBlock) cudaFree(h->dPeerBlock);
+    if (h->dPeerCounter) cudaFree(h->dPeerCounter);
+    if (h->dPeerStatus) cudaFree(h->dPeerStatus);
     double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
                       h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dG, h->dZ, h->dSigma, h->dMean,
                       h->dVar, h->dJ, h->dCov, h->dU, h->dKinv, h->dGradPart, h->dGrad};
@@ -582,6 +591,7 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
     }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "tri_variant")) { h->opt_tri_variant = (int)value; return GPMPC_OK; }
+    if (!strcmp(name, "peer")) { h->opt_peer = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "leaf_variant")) { h->opt_leaf_variant = (int)value; return GPMPC_OK; }
     set_error(h, "unknown option %s", name);
     return GPMPC_ERR_ARG;
@@ -703,6 +713,21 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
     const int np = h->Npad, Nx = h->Nx;
     const int ksplit = choose_ksplit(h);
     const int nblk_mj = (np + KS_CHUNK - 1) / KS_CHUNK, nblk_sq = (np + 255) / 256;
+    // fused epilogue + all-gather over peer memory when the exchange block is attached
+    const int use_peers = (h->world > 1 && h->peer_ready && h->opt_peer && H <= h->peerHcap) ? 1 : 0;
+    PeerArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    if (use_peers) {
+        h->peer_step += 1;
+        for (int r = 0; r < h->world; ++r) pa.base[r] = h->peerBase[r];
+        pa.world = h->world; pa.rank = h->rank;
+        pa.goff = 2 * GPMPC_MAXW + (long long)(h->peer_step & 1) * h->peerGsz;
+        pa.flag_idx = (int)(h->peer_step & 1) * GPMPC_MAXW + h->rank;
+        pa.step = h->peer_step;
+        pa.counter = h->dPeerCounter;
+        pa.total_blocks = (unsigned int)H * h->nloc;
+        CUDA_TRY(cudaMemsetAsync(h->dPeerCounter, 0, sizeof(unsigned int), h->st));
+    }
     for (int h0 = 0; h0 < H; h0 += HB) {
         const int Hc = std::min(HB, H - h0);
         const int bm = (Hc + 7) / 8 * 8;
@@ -733,18 +758,37 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
         }
         dim3 gf(Hc, h->nloc);
         finalize_local_kernel<<<gf, 64, 0, h->st>>>(h->dPMJ, nblk_mj, h->dSQ, nblk_sq, h->dHyp, Nx + 2, Nx, Hc,
-                                                     h->dG, h->a0, H, h0);
+                                                     h->dG, h->a0, H, h0, pa, use_peers);
         CUDA_TRY(cudaGetLastError());
     }
-    if (h->world > 1) {
+    const double* Gsrc = h->dG;
+    const unsigned long long* flags = nullptr;
+    if (use_peers) {
+        Gsrc = h->dPeerBlock + pa.goff;
+        flags = reinterpret_cast<const unsigned long long*>(h->dPeerBlock) + (h->peer_step & 1) * GPMPC_MAXW;
+    } else if (h->world > 1) {
         const size_t cnt = (size_t)h->nloc_max * H * (Nx + 2);
         int r = g_nccl.AllGather(h->dG + (size_t)h->rank * cnt, h->dG, cnt, 8 /* ncclFloat64 */, h->comm, h->st);
         if (r) { set_error(h, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GPMPC_ERR_NCCL; }
     }
     const int smem = (2 * h->Ny * Nx + h->Ny) * 8;
-    assemble_kernel<<<H, 128, smem, h->st>>>(h->dG, h->Ny, Nx, H, method == GPMPC_METHOD_TA, dSigma, spp,
-                                              d_mean, d_var, d_jac, d_cov);
+    assemble_kernel<<<H, 128, smem, h->st>>>(Gsrc, h->Ny, Nx, H, method == GPMPC_METHOD_TA, dSigma, spp,
+                                              d_mean, d_var, d_jac, d_cov, flags, h->world, h->peer_step, h->dPeerStatus);
     CUDA_TRY(cudaGetLastError());
+    return GPMPC_OK;
+}
+
+// after a stream sync: did a consumer give up waiting for a peer's flag?
+static int peer_status_check(gpmpc_handle_t h)
+{
+    if (!h->peer_ready) return GPMPC_OK;
+    int st = 0;
+    CUDA_TRY(cudaMemcpy(&st, h->dPeerStatus, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) {
+        set_error(h, "peer exchange timed out waiting for rank %d (step %llu)", st - 1, h->peer_step);
+        cudaMemset(h->dPeerStatus, 0, sizeof(int));
+        return GPMPC_ERR_NCCL;
+    }
     return GPMPC_OK;
 }
 
@@ -800,6 +844,7 @@ extern "C" int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* 
     if (jac) CUDA_TRY(cudaMemcpyAsync(po + 2 * nm, h->dJ, nj * 8, cudaMemcpyDeviceToHost, h->st));
     if (cov) CUDA_TRY(cudaMemcpyAsync(po + 2 * nm + nj, h->dCov, nc * 8, cudaMemcpyDeviceToHost, h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
+    { int prc = peer_status_check(h); if (prc) return prc; }
     if (mean) memcpy(mean, po, nm * 8);
     if (var) memcpy(var, po + nm, nm * 8);
     if (jac) memcpy(jac, po + 2 * nm, nj * 8);
@@ -883,6 +928,43 @@ extern "C" int gpmpc_comm_init(gpmpc_handle_t h, const void* id128, int rank, in
     return GPMPC_OK;
 }
 
+extern "C" int gpmpc_peer_export(gpmpc_handle_t h, int Hcap, void* handle64)
+{
+    if (!h || !handle64 || Hcap < 1) return GPMPC_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->world > GPMPC_MAXW) { set_error(h, "peer exchange supports at most %d ranks", GPMPC_MAXW); return GPMPC_ERR_ARG; }
+    if (h->dPeerBlock) { set_error(h, "gpmpc_peer_export: already exported"); return GPMPC_ERR_STATE; }
+    const int nyp = h->nloc_max * h->world;
+    h->peerGsz = (long long)nyp * Hcap * (h->Nx + 2);
+    h->peerHcap = Hcap;
+    ALLOC(h->dPeerBlock, 2 * GPMPC_MAXW + 2 * h->peerGsz);
+    ALLOC(h->dPeerCounter, 1);
+    if (!h->dPeerStatus) ALLOC(h->dPeerStatus, 1);
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    cudaIpcMemHandle_t mh;
+    CUDA_TRY(cudaIpcGetMemHandle(&mh, h->dPeerBlock));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64, &mh, 64);
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_peer_attach(gpmpc_handle_t h, const void* handles)
+{
+    if (!h || !handles) return GPMPC_ERR_ARG;
+    if (!h->dPeerBlock) { set_error(h, "gpmpc_peer_attach: call gpmpc_peer_export first"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) { h->peerBase[r] = h->dPeerBlock; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char*)handles + 64 * r, 64);
+        void* ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peerBase[r] = (double*)ptr; h->peerOpened[r] = true;
+    }
+    h->peer_ready = true; h->peer_step = 0;
+    return GPMPC_OK;
+}
+
 extern "C" void* gpmpc_stream(gpmpc_handle_t h) { return h ? (void*)h->st : nullptr; }
 
 extern "C" int gpmpc_synchronize(gpmpc_handle_t h)
@@ -890,7 +972,7 @@ extern "C" int gpmpc_synchronize(gpmpc_handle_t h)
     if (!h) return GPMPC_ERR_ARG;
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->st));
-    return GPMPC_OK;
+    return peer_status_check(h);
 }
 
 // ------------------------------------------------------------------------------------

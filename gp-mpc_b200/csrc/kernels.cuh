@@ -684,25 +684,61 @@ reduce_sq_kernel(const double* __restrict__ Part, int ldp, long long sPart, long
 
 // stage 4: per local output and test point: [mean, var, J_0..J_{Nx-1}] into the gather
 // buffer G[slot][h][2+Nx]  (slot = global output index; one contiguous chunk per rank)
+#define GPMPC_MAXW 16
+// Peer ("fused epilogue + all-gather") mode: instead of writing into the local gather buffer and
+// calling ncclAllGather, every rank stores its [mean,var,J] records directly into the gather
+// buffer of EVERY rank (peer pointers mapped with CUDA IPC, NVLink/NVSwitch P2P stores), then the
+// last block to finish publishes a per-source flag on every peer (release at system scope).
+// The consumer (assemble_kernel) acquires all `world` flags before reading.  Buffers are
+// double-buffered by step parity; in-order streams make that sufficient.
+struct PeerArgs {
+    double* base[GPMPC_MAXW];         // peer-mapped base of each rank's exchange block (own = local)
+    int world, rank;
+    long long goff;                   // offset (doubles) of this step's gather buffer inside the block
+    int flag_idx;                     // parity * GPMPC_MAXW + rank
+    unsigned long long step;
+    unsigned int* counter;            // local completion counter (zeroed at the start of the step)
+    unsigned int total_blocks;
+};
+
 __global__ void finalize_local_kernel(const double* __restrict__ PMJ, int nblk_mj,
                                       const double* __restrict__ SQ, int nblk_sq,
                                       const double* __restrict__ hyp, int hyp_ld, int Nx, int Hc,
-                                      double* __restrict__ G, int slot0, int Htot, int h0)
+                                      double* __restrict__ G, int slot0, int Htot, int h0,
+                                      const PeerArgs pa, int use_peers)
 {
     const int a = blockIdx.y, h = blockIdx.x, q = threadIdx.x;   // q in [0, Nx+1]
-    if (q > Nx + 1) return;
-    double* out = G + (((long long)(slot0 + a)) * Htot + h0 + h) * (Nx + 2);
+    const long long off = (((long long)(slot0 + a)) * Htot + h0 + h) * (Nx + 2);
+    double val = 0.0; int dst = -1;
     if (q <= Nx) {
         const double* p = PMJ + (((long long)a * Hc + h) * nblk_mj) * (Nx + 1) + q;
         double s = 0.0;
         for (int b = 0; b < nblk_mj; ++b) s += p[(long long)b * (Nx + 1)];
-        out[q == 0 ? 0 : q + 1] = s;
-    } else {
+        val = s; dst = (q == 0) ? 0 : q + 1;
+    } else if (q == Nx + 1) {
         const double* p = SQ + ((long long)a * Hc + h) * nblk_sq;
         double s = 0.0;
         for (int b = 0; b < nblk_sq; ++b) s += p[b];
         const double sf = hyp[(long long)a * hyp_ld + Nx];
-        out[1] = sf * sf - s;
+        val = sf * sf - s; dst = 1;
+    }
+    if (!use_peers) {
+        if (dst >= 0) G[off + dst] = val;
+        return;
+    }
+    if (dst >= 0)
+        for (int r = 0; r < pa.world; ++r) pa.base[r][pa.goff + off + dst] = val;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(pa.counter, 1u);
+        if (done == pa.total_blocks - 1) {           // every block's stores are fenced: publish
+            __threadfence_system();
+            for (int r = 0; r < pa.world; ++r) {
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(pa.base[r]) + pa.flag_idx;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(pa.step) : "memory");
+            }
+        }
     }
 }
 
@@ -712,11 +748,25 @@ __global__ void finalize_local_kernel(const double* __restrict__ PMJ, int nblk_m
 __global__ void assemble_kernel(const double* __restrict__ G, int Ny, int Nx, int H, int method_ta,
                                 const double* __restrict__ Sigma, int sigma_per_point,
                                 double* __restrict__ mean, double* __restrict__ var,
-                                double* __restrict__ J, double* __restrict__ cov)
+                                double* __restrict__ J, double* __restrict__ cov,
+                                const unsigned long long* __restrict__ flags, int world,
+                                unsigned long long step, int* __restrict__ status)
 {
     extern __shared__ double sh[];          // Jh[Ny][Nx], JS[Ny][Nx], varh[Ny]
     double* Jh = sh; double* JS = sh + Ny * Nx; double* vh = sh + 2 * Ny * Nx;
     const int h = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+    if (flags) {      // peer mode: acquire every source rank's flag for this step (bounded spin)
+        if (tid < world) {
+            const long long t0 = clock64();
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + tid) : "memory");
+                if (v >= step) break;
+                if (clock64() - t0 > 8000000000LL) { atomicExch(status, 1 + tid); break; }   // ~4 s
+            } while (true);
+        }
+        __syncthreads();
+    }
     for (int idx = tid; idx < Ny * Nx; idx += nth) {
         const int a = idx / Nx, d = idx % Nx;
         const double v = G[(((long long)a) * H + h) * (Nx + 2) + 2 + d];

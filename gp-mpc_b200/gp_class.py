@@ -122,6 +122,10 @@ class GP:
             uid = self.__engine_factory.comm_unique_id() if c.rank == 0 else None
             uid = c.broadcast_object(uid, src=0)
             self.__engine.comm_init(uid, c.rank, c.world)
+            # fused epilogue + all-gather over NVLink peer memory (CUDA IPC); NCCL stays the fallback
+            if hasattr(self.__engine, 'peer_export') and os.environ.get('GPMPC_NO_PEER', '0') != '1':
+                handles = c.allgather_object(self.__engine.peer_export(int(os.environ.get('GPMPC_PEER_HCAP', 256))))
+                self.__engine.peer_attach(handles)
 
     def __factorize(self):
         self.__engine.set_hyper(self.__hyper)

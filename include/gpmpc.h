@@ -133,6 +133,15 @@ int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value);
 int gpmpc_comm_unique_id(void* id128);
 int gpmpc_comm_init(gpmpc_handle_t h, const void* id128, int rank, int world);
 
+/* Fused epilogue + all-gather over NVLink peer memory (optional, after gpmpc_comm_init):
+ * every rank exports one exchange block (gpmpc_peer_export -> 64-byte CUDA IPC handle, room
+ * for Hcap test points), the handles of ALL ranks (world x 64 bytes, rank order) are passed
+ * to gpmpc_peer_attach.  gpmpc_predict* then stores each rank's results directly into every
+ * peer's buffer from the predict epilogue and synchronises with flags; ncclAllGather remains
+ * the fallback (H > Hcap, option "peer" = 0, or no attach). */
+int gpmpc_peer_export(gpmpc_handle_t h, int Hcap, void* handle64);
+int gpmpc_peer_attach(gpmpc_handle_t h, const void* handles);
+
 /* The handle's CUDA stream (cudaStream_t) so a caller can record events on it. */
 void* gpmpc_stream(gpmpc_handle_t h);
 int gpmpc_synchronize(gpmpc_handle_t h);
