@@ -31,7 +31,7 @@ for peer in ('0', '1'):
     report('tank peer=%s mode/owned=%s' % (peer, list(gp.engine.local_outputs)), mean=relinf(mean, d['mean_ta']), cov=relinf(cov, d['cov_ta']), chol=relinf(chol, m['chol']) * 1e3)
     gp.close()
     # synthetic, many steps back to back (exercises the double-buffered flags), H > 64 chunks too
-    for (N, Nx, Ny, H) in [(1000, 8, 8, 50), (700, 6, 8, 130), (500, 5, 3, 9)]:
+    for (N, Nx, Ny, H) in [(1000, 10, 8, 50), (700, 10, 8, 130), (500, 5, 3, 9)]:
         p = orc.synthetic_problem(N, Nx, Ny, config_id=N, H=H)
         post = orc.postfit(p['X'], p['Y'], p['hyper'], lapack_general_solve=False)
         mo, vo = orc.gp_mean_var(p['X'], p['hyper'], post['alpha'], post['chol'], p['Z'])
