@@ -17,6 +17,8 @@ if which in ('all', 'kbuild'):
     print('kbuild_full ms', eng.profile(L.PROF_KBUILD_FULL, reps=1))
 if which in ('all', 'syrk'):
     print('syrk ms', eng.profile(L.PROF_SYRK, reps=1))
+if which == 'factor':
+    eng.factorize()
 if which in ('all', 'trigemm'):
     eng.factorize()
     eng.predict(w['Z'], w['Sigma'], L.METHOD_TA)
