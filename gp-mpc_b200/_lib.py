@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GPMPC_LIB', os.path.join(_HERE, 'lib', 'libgpmpc.so'))
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NCCL, ERR_NOTPD = 0, -1, -2, -3, -4, -5
-METHOD_ME, METHOD_TA = 0, 1
+METHOD_ME, METHOD_TA, METHOD_EM = 0, 1, 2
 GET_CHOL, GET_ALPHA, GET_INVK, GET_K, GET_LOGDET, GET_LINV = range(6)
 PROF_KBUILD_FULL, PROF_KBUILD_LOWER, PROF_SYRK, PROF_FACTORIZE, PROF_TRIGEMM = range(5)
 

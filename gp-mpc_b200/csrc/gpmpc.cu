@@ -77,6 +77,10 @@ struct gpmpc_handle_s {
     // nlml scratch
     double *dU = nullptr, *dKinv = nullptr, *dGradPart = nullptr, *dGrad = nullptr;
     bool has_data = false, has_hyper = false, factorized = false;
+    // EM scratch
+    double *dKinvAll = nullptr, *dEMP = nullptr, *dEmE = nullptr, *dEmF = nullptr, *dEmW = nullptr, *dEmIJ = nullptr;
+    double *dEmMeanPart = nullptr, *dEmPart = nullptr;
+    bool em_kinv_valid = false; int emHcap = 0;
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
@@ -344,7 +348,8 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     if (h->dPeerStatus) cudaFree(h->dPeerStatus);
     double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
                       h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dG, h->dZ, h->dSigma, h->dMean,
-                      h->dVar, h->dJ, h->dCov, h->dU, h->dKinv, h->dGradPart, h->dGrad};
+                      h->dVar, h->dJ, h->dCov, h->dU, h->dKinv, h->dGradPart, h->dGrad,
+                      h->dKinvAll, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
     if (h->hPinned) cudaFreeHost(h->hPinned);
@@ -488,7 +493,7 @@ extern "C" int gpmpc_factorize(gpmpc_handle_t h, double jitter, int* info)
     CUDA_TRY(cudaMemcpyAsync(res.data(), h->dRes, 2 * nl * 8, cudaMemcpyDeviceToHost, h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
     for (int a = 0; a < nl; ++a) { h->logdet[a] = res[2 * a]; h->yalpha[a] = res[2 * a + 1]; }
-    h->factorized = true;
+    h->factorized = true; h->em_kinv_valid = false;
     return GPMPC_OK;
 }
 
@@ -778,6 +783,146 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
     return GPMPC_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// 'EM' exact moment matching (gp_functions.py:344-418): small dense helpers on the host
+// (Nx <= 32), everything O(N), O(N^2) on the GPU
+// ------------------------------------------------------------------------------------
+static bool lu_factor(int n, double* A, int* piv, double* det)
+{
+    double d = 1.0;
+    for (int k = 0; k < n; ++k) {
+        int p = k; double mx = fabs(A[k * n + k]);
+        for (int i = k + 1; i < n; ++i) if (fabs(A[i * n + k]) > mx) { mx = fabs(A[i * n + k]); p = i; }
+        piv[k] = p;
+        if (mx == 0.0) { *det = 0.0; return false; }
+        if (p != k) { for (int j = 0; j < n; ++j) std::swap(A[k * n + j], A[p * n + j]); d = -d; }
+        d *= A[k * n + k];
+        for (int i = k + 1; i < n; ++i) {
+            const double f = A[i * n + k] / A[k * n + k];
+            A[i * n + k] = f;
+            for (int j = k + 1; j < n; ++j) A[i * n + j] -= f * A[k * n + j];
+        }
+    }
+    *det = d;
+    return true;
+}
+
+static void lu_solve(int n, const double* LU, const int* piv, double* B, int m)
+{
+    for (int k = 0; k < n; ++k) if (piv[k] != k) for (int j = 0; j < m; ++j) std::swap(B[k * m + j], B[piv[k] * m + j]);
+    for (int k = 0; k < n; ++k)
+        for (int i = k + 1; i < n; ++i) { const double f = LU[i * n + k]; for (int j = 0; j < m; ++j) B[i * m + j] -= f * B[k * m + j]; }
+    for (int k = n - 1; k >= 0; --k) {
+        for (int j = 0; j < m; ++j) B[k * m + j] /= LU[k * n + k];
+        for (int i = 0; i < k; ++i) { const double f = LU[i * n + k]; for (int j = 0; j < m; ++j) B[i * m + j] -= f * B[k * m + j]; }
+    }
+}
+
+// pack the per-output / per-pair Nx x Nx quantities of one test point (layout: kernels.cuh)
+static int em_prepare_point(gpmpc_handle_t h, const double* S, double* out)
+{
+    const int Nx = h->Nx, Ny = h->Ny, nn = Nx * Nx, m = Nx + 2;
+    std::vector<double> R(nn), B(nn);
+    std::vector<int> piv(Nx);
+    double det = 0.0;
+    for (int a = 0; a < Ny; ++a) {
+        const double* hp = &h->hyper[(size_t)a * m];
+        for (int i = 0; i < Nx; ++i) for (int j = 0; j < Nx; ++j) R[i * Nx + j] = S[i * Nx + j] + (i == j ? hp[i] * hp[i] : 0.0);
+        if (!lu_factor(Nx, R.data(), piv.data(), &det) || !(det > 0.0)) { set_error(h, "EM: Sigma + Lambda is not positive definite"); return GPMPC_ERR_ARG; }
+        for (int i = 0; i < nn; ++i) B[i] = 0.0;
+        for (int i = 0; i < Nx; ++i) B[i * Nx + i] = 1.0;
+        lu_solve(Nx, R.data(), piv.data(), B.data(), Nx);                 // iR = (Sigma + Lambda)^-1   (:383-385)
+        double* o = out + (size_t)a * (nn + 1);
+        memcpy(o, B.data(), nn * 8);
+        double pe = 1.0;
+        for (int d = 0; d < Nx; ++d) pe *= hp[d];
+        o[nn] = hp[Nx] * hp[Nx] / sqrt(det) * pe;                         // c (:386-387)
+    }
+    int p = 0;
+    for (int a = 0; a < Ny; ++a)
+        for (int b = 0; b <= a; ++b, ++p) {
+            const double* ha = &h->hyper[(size_t)a * m];
+            const double* hb = &h->hyper[(size_t)b * m];
+            for (int i = 0; i < Nx; ++i)
+                for (int j = 0; j < Nx; ++j)
+                    R[i * Nx + j] = S[i * Nx + j] * (1.0 / (ha[j] * ha[j]) + 1.0 / (hb[j] * hb[j])) + (i == j ? 1.0 : 0.0);   // :396-397
+            if (!lu_factor(Nx, R.data(), piv.data(), &det) || !(det > 0.0)) { set_error(h, "EM: det(R_ab) <= 0"); return GPMPC_ERR_ARG; }
+            for (int i = 0; i < nn; ++i) B[i] = 0.5 * S[i];
+            lu_solve(Nx, R.data(), piv.data(), B.data(), Nx);             // solve(R, Sigma/2)  (:402)
+            double* o = out + (size_t)Ny * (nn + 1) + (size_t)p * (nn + 3);
+            memcpy(o, B.data(), nn * 8);
+            o[nn] = 1.0 / sqrt(det); o[nn + 1] = a; o[nn + 2] = b;        // t (:398)
+        }
+    return GPMPC_OK;
+}
+
+template <int NXP>
+static cudaError_t launch_em_prep(gpmpc_handle_t h, int npairs, const double* dz, const double* dEMP, int nblk)
+{
+    dim3 g(nblk, h->Ny + npairs);
+    em_prep_kernel<NXP><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->Ny, npairs, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
+                                              dz, dEMP, h->dEmMeanPart, nblk, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->Npad);
+    return cudaGetLastError();
+}
+
+static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Sigma, int spp,
+                      double* mean, double* var, double* cov)
+{
+    const int Nx = h->Nx, Ny = h->Ny, nn = Nx * Nx, np = h->Npad;
+    if (h->nloc != Ny) { set_error(h, "EM needs all outputs on one handle (replicate the model, shard the points)"); return GPMPC_ERR_STATE; }
+    if (!Sigma) { set_error(h, "EM needs an input covariance"); return GPMPC_ERR_ARG; }
+    const int npairs = Ny * (Ny + 1) / 2;
+    if (npairs > 1024) { set_error(h, "EM supports Ny <= 44"); return GPMPC_ERR_ARG; }
+    const size_t per = (size_t)Ny * (nn + 1) + (size_t)npairs * (nn + 3);
+    const int nblk = (np + 255) / 256, T = (h->N + 63) / 64;
+    if (!h->dKinvAll) {
+        ALLOC(h->dKinvAll, (long long)Ny * slab(h));
+        ALLOC(h->dEmE, (long long)npairs * np); ALLOC(h->dEmF, (long long)npairs * np);
+        ALLOC(h->dEmW, (long long)npairs * Nx * np); ALLOC(h->dEmIJ, (long long)npairs * Nx * np);
+        ALLOC(h->dEmMeanPart, (long long)Ny * nblk); ALLOC(h->dEmPart, (long long)npairs * T * T);
+    }
+    if (H > h->emHcap) {
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (h->dEMP) cudaFree(h->dEMP);
+        h->dEMP = nullptr;
+        ALLOC(h->dEMP, (long long)H * per);
+        h->emHcap = H;
+    }
+    if (!h->em_kinv_valid) {       // beta beta^T - K^-1 needs the dense inverse (:409-411)
+        for (int a = 0; a < Ny; ++a) {
+            int rc = compute_kinv(h, a);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(h->dKinvAll + (long long)a * slab(h), h->dKinv, slab(h) * 8, cudaMemcpyDeviceToDevice, h->st));
+        }
+        h->em_kinv_valid = true;
+    }
+    std::vector<double> emp((size_t)H * per);
+    for (int p = 0; p < H; ++p) {
+        int rc = em_prepare_point(h, Sigma + (spp ? (size_t)p * nn : 0), emp.data() + (size_t)p * per);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->dEMP, emp.data(), emp.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CUDA_TRY(cudaMemcpyAsync(h->dZ, Z, (size_t)H * Nx * 8, cudaMemcpyHostToDevice, h->st));
+    for (int p = 0; p < H; ++p) {
+        const double* dz = h->dZ + (size_t)p * Nx;
+        const double* dP = h->dEMP + (size_t)p * per;
+        cudaError_t e = (Nx <= 8) ? launch_em_prep<8>(h, npairs, dz, dP, nblk)
+                      : (Nx <= 16) ? launch_em_prep<16>(h, npairs, dz, dP, nblk) : launch_em_prep<32>(h, npairs, dz, dP, nblk);
+        CUDA_TRY(e);
+        em_pair_kernel<<<dim3(T, T, npairs), 256, 2 * Nx * 64 * 8, h->st>>>(h->N, Nx, Ny, dP, h->dAlpha, np, h->dKinvAll, np, slab(h),
+                                                                          h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmPart);
+        CUDA_TRY(cudaGetLastError());
+        em_finalize_kernel<<<1, 1024, 0, h->st>>>(Nx, Ny, npairs, dP, h->dHyp, Nx + 2, h->dEmMeanPart, nblk, h->dEmPart, T * T,
+                                                   h->dMean + (size_t)p * Ny, h->dVar + (size_t)p * Ny, h->dCov + (size_t)p * Ny * Ny);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (mean) CUDA_TRY(cudaMemcpyAsync(mean, h->dMean, (size_t)H * Ny * 8, cudaMemcpyDeviceToHost, h->st));
+    if (var) CUDA_TRY(cudaMemcpyAsync(var, h->dVar, (size_t)H * Ny * 8, cudaMemcpyDeviceToHost, h->st));
+    if (cov) CUDA_TRY(cudaMemcpyAsync(cov, h->dCov, (size_t)H * Ny * Ny * 8, cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return GPMPC_OK;
+}
+
 // after a stream sync: did a consumer give up waiting for a peer's flag?
 static int peer_status_check(gpmpc_handle_t h)
 {
@@ -797,7 +942,7 @@ static int predict_check(gpmpc_handle_t h, int method, int H)
     if (!h) return GPMPC_ERR_ARG;
     if (!h->factorized) { set_error(h, "gpmpc_predict: call gpmpc_factorize first"); return GPMPC_ERR_STATE; }
     if (H < 1) { set_error(h, "gpmpc_predict: H < 1"); return GPMPC_ERR_ARG; }
-    if (method != GPMPC_METHOD_ME && method != GPMPC_METHOD_TA) { set_error(h, "gpmpc_predict: unknown method %d", method); return GPMPC_ERR_ARG; }
+    if (method != GPMPC_METHOD_ME && method != GPMPC_METHOD_TA && method != GPMPC_METHOD_EM) { set_error(h, "gpmpc_predict: unknown method %d", method); return GPMPC_ERR_ARG; }
     return GPMPC_OK;
 }
 
@@ -806,6 +951,7 @@ extern "C" int gpmpc_predict_device(gpmpc_handle_t h, int method, int H, const d
 {
     int rc = predict_check(h, method, H);
     if (rc) return rc;
+    if (method == GPMPC_METHOD_EM) { set_error(h, "gpmpc_predict_device: EM needs host inputs (use gpmpc_predict)"); return GPMPC_ERR_ARG; }
     if (!dZ || (method == GPMPC_METHOD_TA && d_cov && !dSigma)) { set_error(h, "gpmpc_predict_device: null Z / Sigma"); return GPMPC_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(h->device));
     rc = ensure_predict_bufs(h, H);
@@ -825,6 +971,10 @@ extern "C" int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* 
     CUDA_TRY(cudaSetDevice(h->device));
     rc = ensure_predict_bufs(h, H);
     if (rc) return rc;
+    if (method == GPMPC_METHOD_EM) {
+        if (jac) { set_error(h, "gpmpc_predict: EM does not return a Jacobian"); return GPMPC_ERR_ARG; }
+        return predict_em(h, H, Z, Sigma, spp, mean, var, cov);
+    }
     const int Nx = h->Nx, Ny = h->Ny;
     const size_t nz = (size_t)H * Nx, ns = (method == GPMPC_METHOD_TA && Sigma) ? (size_t)(spp ? H : 1) * Nx * Nx : 0;
     const size_t nm = (size_t)H * Ny, nj = (size_t)H * Ny * Nx, nc = (size_t)H * Ny * Ny;

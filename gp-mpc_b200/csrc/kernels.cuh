@@ -942,3 +942,179 @@ gram_cov_kernel(const double* __restrict__ V, int ldv, long long sV, int n,
         out[((long long)a * H + h2) * H + h1] = c;
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// 'EM' exact moment matching  (gp_exact_moment, gp_functions.py:344-418), one test point
+// per launch set.  Host prepares the Nx x Nx quantities (gpmpc.cu, em_prepare_point):
+//   per output a :  iR_a = (Sigma + Lambda_a)^-1 ,  c_a = sf2_a prod(ell_a) / sqrt(det(Sigma+Lambda_a))
+//   per pair a>=b:  Qm = (Sigma (iL_a+iL_b) + I)^-1 Sigma/2 ,  t_ab = det(...)^-1/2
+// EMP layout (doubles): [a: iR (Nx*Nx), c] * Ny, then [pair: Qm (Nx*Nx), t, a, b] * npairs
+// ---------------------------------------------------------------------------------------
+template <int NXP>
+__global__ void __launch_bounds__(256)
+em_prep_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, int Ny, int npairs,
+               const double* __restrict__ hyp, int hyp_ld, const double* __restrict__ alpha, long long sal,
+               const double* __restrict__ z, const double* __restrict__ EMP,
+               double* __restrict__ meanPart, int nblk,
+               double* __restrict__ E, double* __restrict__ F, double* __restrict__ W, double* __restrict__ IJ, int ldn)
+{
+    __shared__ double M[NXP * NXP];
+    __shared__ double red[8];
+    const int role = blockIdx.y, tid = threadIdx.x;
+    const int i = blockIdx.x * 256 + tid;
+    const int nn = Nx * Nx;
+    double v[NXP];
+#pragma unroll
+    for (int d = 0; d < NXP; ++d) v[d] = (d < Nx && i < N) ? XT[(long long)d * ldx + i] - z[d] : 0.0;
+    if (role < Ny) {                                        // mean of output a (:381-388)
+        const int a = role;
+        const double* P = EMP + (long long)a * (nn + 1);
+        for (int q = tid; q < nn; q += 256) M[q] = P[q];
+        __syncthreads();
+        double quad = 0.0;
+#pragma unroll
+        for (int d = 0; d < NXP; ++d) {
+            if (d < Nx) {
+                double tacc = 0.0;
+#pragma unroll
+                for (int e = 0; e < NXP; ++e) if (e < Nx) tacc = fma(M[d * Nx + e], v[e], tacc);
+                quad = fma(v[d], tacc, quad);
+            }
+        }
+        double q = (i < N) ? P[nn] * exp(-0.5 * quad) * alpha[(long long)a * sal + i] : 0.0;
+        q = warp_sum(q);
+        if ((tid & 31) == 0) red[tid >> 5] = q;
+        __syncthreads();
+        if (tid == 0) {
+            double r = 0.0;
+            for (int w = 0; w < 8; ++w) r += red[w];
+            meanPart[(long long)a * nblk + blockIdx.x] = r;
+        }
+        return;
+    }
+    const int p = role - Ny;
+    const double* P = EMP + (long long)Ny * (nn + 1) + (long long)p * (nn + 3);
+    const int a = (int)P[nn + 1], b = (int)P[nn + 2];
+    for (int q = tid; q < nn; q += 256) M[q] = P[q];
+    __syncthreads();
+    if (i >= ldn) return;
+    const double* ha = hyp + (long long)a * hyp_ld;
+    const double* hb = hyp + (long long)b * hyp_ld;
+    double lka = 2.0 * log(ha[Nx]), lkb = 2.0 * log(hb[Nx]);      // log_k (:389-391)
+    double ii[NXP], ij[NXP];
+#pragma unroll
+    for (int d = 0; d < NXP; ++d) {
+        ii[d] = 0.0; ij[d] = 0.0;
+        if (d < Nx) {
+            const double sa = v[d] / ha[d], sb = v[d] / hb[d];
+            lka = fma(-0.5 * sa, sa, lka); lkb = fma(-0.5 * sb, sb, lkb);
+            ii[d] = v[d] / (ha[d] * ha[d]); ij[d] = v[d] / (hb[d] * hb[d]);
+        }
+    }
+    double ei = lka, fj = lkb;
+#pragma unroll
+    for (int e = 0; e < NXP; ++e) {
+        if (e < Nx) {
+            double wi = 0.0, wj = 0.0;
+#pragma unroll
+            for (int d = 0; d < NXP; ++d) if (d < Nx) { wi = fma(ii[d], M[d * Nx + e], wi); wj = fma(ij[d], M[d * Nx + e], wj); }
+            ei = fma(wi, ii[e], ei); fj = fma(wj, ij[e], fj);
+            W[((long long)p * Nx + e) * ldn + i] = wi;
+            IJ[((long long)p * Nx + e) * ldn + i] = ij[e];
+        }
+    }
+    E[(long long)p * ldn + i] = ei;
+    F[(long long)p * ldn + i] = fj;
+}
+
+// sum_ij A_ij Q_ij for one pair; 64x64 tile per CTA, 4x4 per thread (:394-412)
+__global__ void __launch_bounds__(256)
+em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
+               const double* __restrict__ alpha, long long sal, const double* __restrict__ KinvAll, int ldk, long long sKinv,
+               const double* __restrict__ E, const double* __restrict__ F, const double* __restrict__ W,
+               const double* __restrict__ IJ, int ldn, double* __restrict__ part)
+{
+    extern __shared__ double sm[];
+    double* Ws = sm; double* Js = sm + Nx * 64;
+    __shared__ double red[8];
+    const int p = blockIdx.z, nn = Nx * Nx;
+    const double* P = EMP + (long long)Ny * (nn + 1) + (long long)p * (nn + 3);
+    const int a = (int)P[nn + 1], b = (int)P[nn + 2];
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int idx = tid; idx < Nx * 64; idx += 256) {
+        const int d = idx >> 6, r = idx & 63;
+        Ws[idx] = W[((long long)p * Nx + d) * ldn + i0 + r];
+        Js[idx] = IJ[((long long)p * Nx + d) * ldn + j0 + r];
+    }
+    __syncthreads();
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    for (int d = 0; d < Nx; ++d) {
+        double wv[4], jv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) wv[r] = Ws[d * 64 + ty + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) jv[c] = Js[d * 64 + tx + 16 * c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv[r], jv[c], acc[r][c]);
+    }
+    const double* Kinv = KinvAll + (long long)a * sKinv;
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 16 * r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + tx + 16 * c;
+            if (i < N && j < N) {
+                const double q = exp(E[(long long)p * ldn + i] + F[(long long)p * ldn + j] + 2.0 * acc[r][c]);
+                double A = alpha[(long long)a * sal + i] * alpha[(long long)b * sal + j];
+                if (a == b) A -= Kinv[(long long)max(i, j) * ldk + min(i, j)];
+                s = fma(A, q, s);
+            }
+        }
+    }
+    s = warp_sum(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double r = 0.0;
+        for (int w = 0; w < 8; ++w) r += red[w];
+        part[((long long)p * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = r;
+    }
+}
+
+// mean (Ny), cov (Ny,Ny): t_ab * sum (+ sf2 on the diagonal) - mean mean^T   (:412-416)
+__global__ void em_finalize_kernel(int Nx, int Ny, int npairs, const double* __restrict__ EMP,
+                                   const double* __restrict__ hyp, int hyp_ld,
+                                   const double* __restrict__ meanPart, int nblk,
+                                   const double* __restrict__ part, int ntile2,
+                                   double* __restrict__ mean, double* __restrict__ var, double* __restrict__ cov)
+{
+    __shared__ double mu[64];
+    const int tid = threadIdx.x, nn = Nx * Nx;
+    if (tid < Ny) {
+        double s = 0.0;
+        for (int b = 0; b < nblk; ++b) s += meanPart[(long long)tid * nblk + b];
+        mu[tid] = s;
+        if (mean) mean[tid] = s;
+    }
+    __syncthreads();
+    if (tid < npairs) {
+        const double* P = EMP + (long long)Ny * (nn + 1) + (long long)tid * (nn + 3);
+        const int a = (int)P[nn + 1], b = (int)P[nn + 2];
+        double s = 0.0;
+        for (int q = 0; q < ntile2; ++q) s += part[(long long)tid * ntile2 + q];
+        double c = P[nn] * s;
+        if (a == b) { const double sf = hyp[(long long)a * hyp_ld + Nx]; c += sf * sf; }
+        c -= mu[a] * mu[b];
+        if (cov) { cov[a * Ny + b] = c; cov[b * Ny + a] = c; }
+        if (a == b && var) var[a] = c;
+    }
+}

@@ -27,7 +27,7 @@ from .comm import Comm
 from .optimize import train_gp_b200
 from .partition import choose_mode, output_block, point_block
 
-_GPU_METHODS = {'ME': _lib.METHOD_ME, 'TA': _lib.METHOD_TA}
+_GPU_METHODS = {'ME': _lib.METHOD_ME, 'TA': _lib.METHOD_TA, 'EM': _lib.METHOD_EM}
 _KNOWN_METHODS = ('ME', 'TA', 'EM', 'old_ME', 'old_TA')      # gp_class.py:197-205
 
 
@@ -229,15 +229,15 @@ class GP:
     def set_method(self, gp_method='TA'):
         """ Select wich GP function to use  (reference gp_class.py:193-242)
 
-            'ME': Mean Equivalence (normal GP), 'TA': 1st order Taylor Approximation run on
-            the GPU.  'EM' and the deprecated 'old_ME'/'old_TA' are valid names in the
-            reference; they are not part of this engine yet (SURVEY 8f row 2 / out of scope).
+            'ME': Mean Equivalence (normal GP), 'TA': 1st order Taylor Approximation and
+            'EM': exact moment matching run on the GPU.  The deprecated 'old_ME'/'old_TA' are
+            valid names in the reference but out of scope here.
         """
         if gp_method not in _KNOWN_METHODS:
             raise NameError('No GP method called: ' + gp_method)        # gp_class.py:237
         if gp_method not in _GPU_METHODS:
             raise NotImplementedError("gp_method %r is not implemented by the B200 engine "
-                                      "(available: 'ME', 'TA')" % gp_method)
+                                      "(available: 'ME', 'TA', 'EM')" % gp_method)
         self.__gp_method = gp_method
 
     def __predict_std(self, Z, Sigma, method, want_cov=True, want_jac=True):
@@ -265,7 +265,7 @@ class GP:
             x = self.standardize(x, self.__meanX, self.__stdX)
             u = self.standardize(u, self.__meanU, self.__stdU)
         Z = np.hstack([x, u])
-        mean, var, c, _ = self.__predict_std(Z, cov if method == 'TA' else None, method, True, False)
+        mean, var, c, _ = self.__predict_std(Z, cov if method in ('TA', 'EM') else None, method, True, False)
         if self.__normalize:
             mean = self.inverse_mean(mean, self.__meanY, self.__stdY)
         return mean, c

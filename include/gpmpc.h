@@ -40,7 +40,7 @@ enum {
 };
 
 /* propagation method of GP.set_method / GP.predict (gp_class.py:193-237) */
-enum { GPMPC_METHOD_ME = 0, GPMPC_METHOD_TA = 1 };
+enum { GPMPC_METHOD_ME = 0, GPMPC_METHOD_TA = 1, GPMPC_METHOD_EM = 2 /* gp_exact_moment, gp_functions.py:344-418; host API only */ };
 
 /* selector of gpmpc_get */
 enum {

@@ -209,6 +209,40 @@ def test_full_size_properties_n16384():
     eng.close()
 
 
+# ------------------------------------------------------------------ 'EM' exact moment matching (8f row 2)
+def test_exact_moment_matching_vs_restatement():
+    """gp_exact_moment (gp_functions.py:344-418).  The EM covariance subtracts invK from
+    beta beta^T and cancels ~6 digits, so the tight comparison feeds the oracle restatement the
+    SAME invK the GPU uses; the comparison with the stored-model answer is necessarily loose."""
+    m = load_fixture('tank'); d = load_golden('derived', 'tank')
+    eng, _ = _fit_engine(m['X'], m['Y'], m['hyper'])
+    L = _L()
+    invK = np.stack([eng.get(L.GET_INVK, a) for a in range(4)])
+    rng = np.random.default_rng(4)
+    Z = 0.4 * rng.standard_normal((5, 6))
+    A = rng.standard_normal((6, 6)); Sig = 1e-3 * np.eye(6) + 1e-4 * A @ A.T
+    Sg = np.stack([Sig * (1 + 0.3 * h) for h in range(5)])
+    mean, var, cov, _ = eng.predict(Z, Sg, L.METHOD_EM, want_jac=False)
+    for h in range(5):
+        mo, co = orc.gp_exact_moment(invK, m['X'], m['Y'], m['hyper'], Z[h], Sg[h])
+        assert relinf(mean[h], mo) < TOL
+        assert relinf(cov[h], co) < TOL
+        assert np.array_equal(var[h], np.diag(cov[h]))
+    # EM -> ME as the input covariance vanishes (mean exactly, variance up to the invK cancellation)
+    mean0, _, cov0, _ = eng.predict(Z, 1e-14 * np.eye(6), L.METHOD_EM, want_jac=False)
+    mean_me, var_me, _, _ = eng.predict(Z, None, L.METHOD_ME, want_jac=False)
+    assert relinf(mean0, mean_me) < 1e-7
+    assert relinf(np.einsum('haa->ha', cov0), var_me) < 5e-2
+    eng.close()
+    # through the GP class at the example's operating point, against the stored-model answer
+    gp, m = _gp_from_fixture('tank')
+    gp.set_method('EM')
+    mean, cov = gp.predict(d['x0'], d['u0'], d['Sigma'])
+    assert relinf(mean, d['mean_em']) < TOL
+    assert relinf(np.diag(cov), np.diag(d['cov_em'])) < 2e-2
+    gp.close()
+
+
 # ------------------------------------------------------------------ a6/a7 NLML + gradient
 @pytest.mark.parametrize('name', ['tank', 'car'])
 def test_nlml_matches_reference_values(name):
