@@ -19,6 +19,7 @@
 #define HB 64                 // test points per predict pass (rows of the KS^T operand)
 #define MAX_CHUNKS 16         // split-K partial slots per output
 #define NX_MAX 32
+#define MAX_DEPTH 12           // recursion depth bound: 128 * 2^12 rows
 
 // ------------------------------------------------------------------------------------
 // minimal NCCL surface, bound at run time with dlopen (no link-time dependency)
@@ -64,6 +65,9 @@ struct gpmpc_handle_s {
     int nloc_max = 0;                 // ceil(Ny / world): slots per rank in the gather buffer
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // factorisation overlap: step 5a of every recursion depth runs on its own side stream
+    cudaStream_t sideSt[MAX_DEPTH] = {nullptr}; cudaEvent_t evA[MAX_DEPTH] = {nullptr}, evB[MAX_DEPTH] = {nullptr};
+    long long w2off[MAX_DEPTH + 1] = {0}; int opt_overlap = 1;
     // model
     double *dXT = nullptr, *dMu = nullptr, *dY = nullptr, *dHyp = nullptr, *dJit = nullptr, *dHypTmp = nullptr;
     double *dL = nullptr, *dLi = nullptr, *dW1 = nullptr, *dW2 = nullptr;
@@ -104,21 +108,29 @@ static void set_error(gpmpc_handle_t h, const char* fmt, ...)
 
 static inline long long slab(gpmpc_handle_t h) { return (long long)h->Npad * h->Npad; }
 static inline long long wslab(gpmpc_handle_t h) { return (long long)h->Npad * h->Npad / 4 + 128; }
+static inline long long w2slab(gpmpc_handle_t h) { return h->w2off[MAX_DEPTH]; }   // all depths, one batch entry
 
 // ------------------------------------------------------------------------------------
 // GEMM helpers (all operands live in slabs with leading dimension ld)
 // ------------------------------------------------------------------------------------
+static cudaError_t gemm128_on(gpmpc_handle_t h, cudaStream_t st, bool bt, const GemmParams& p, int batch);
+
 // callers describe the problem in 128x128 tiles (mt, nt); variant 1 re-tiles N by 64
 static cudaError_t gemm128(gpmpc_handle_t h, bool bt, const GemmParams& p, int batch)
+{
+    return gemm128_on(h, h->st, bt, p, batch);
+}
+
+static cudaError_t gemm128_on(gpmpc_handle_t h, cudaStream_t st, bool bt, const GemmParams& p, int batch)
 {
     if (h->opt_gemm_variant == 1) {       // 128x64 tiles, 4 warps, 3 stages, 2 CTAs/SM
         GemmParams q = p;
         q.nt = p.nt * 2;
-        return bt ? gemm_launch<128, 64, 2, 2, true, 3, 2>(q, batch, 1, h->st)
-                  : gemm_launch<128, 64, 2, 2, false, 3, 2>(q, batch, 1, h->st);
+        return bt ? gemm_launch<128, 64, 2, 2, true, 3, 2>(q, batch, 1, st)
+                  : gemm_launch<128, 64, 2, 2, false, 3, 2>(q, batch, 1, st);
     }
-    return bt ? gemm_launch<128, 128, 2, 4, true, 4, 1>(p, batch, 1, h->st)
-              : gemm_launch<128, 128, 2, 4, false, 4, 1>(p, batch, 1, h->st);
+    return bt ? gemm_launch<128, 128, 2, 4, true, 4, 1>(p, batch, 1, st)
+              : gemm_launch<128, 128, 2, 4, false, 4, 1>(p, batch, 1, st);
 }
 
 // Recursive blocked Cholesky + triangular inverse on the diagonal block
@@ -130,7 +142,7 @@ static cudaError_t gemm128(gpmpc_handle_t h, bool bt, const GemmParams& p, int b
 //   5. Li21 = -Li22 (L21 Li11)          (two DMMA GEMMs NN)
 // All flops except the 128x128 leaves run on the fp64 tensor pipe.
 static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, long long sLi,
-                         int* dInfo, int off, int n, int batch)
+                         int* dInfo, int off, int n, int batch, int depth = 0)
 {
     const int ld = h->Npad;
     if (n <= LEAF_N) {
@@ -151,7 +163,7 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
     }
     const int nb = n / GPMPC_TILE;
     const int n1 = (nb / 2) * GPMPC_TILE, n2 = n - n1;
-    int rc = potrf_inv_rec(h, A, Li, sA, sLi, dInfo, off, n1, batch);
+    int rc = potrf_inv_rec(h, A, Li, sA, sLi, dInfo, off, n1, batch, depth + 1);
     if (rc) return rc;
     double* A21 = A + (long long)(off + n1) * ld + off;
     double* A22 = A + (long long)(off + n1) * ld + off + n1;
@@ -179,21 +191,36 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
     p.C = A22; p.ldc = ld; p.sC = sA; p.Cin = A22; p.ldcin = ld; p.sCin = sA;
     p.mt = n2 / 128; p.nt = n2 / 128; p.K = n1; p.alpha = -1.0; p.beta = 1.0; p.lower = 1;
     CUDA_TRY(gemm128(h, true, p, batch));
-    // 4.
-    rc = potrf_inv_rec(h, A, Li, sA, sLi, dInfo, off + n1, n2, batch);
-    if (rc) return rc;
-    // 5a. W2 = L21 * Li11     Bop[k][j] = Li11[k][j] != 0 only for k >= j
-    //     (L21 is read from the matrix: the W1 workspace was reused by the recursion in step 4)
+    // 5a. W2 = L21 * Li11     Bop[k][j] = Li11[k][j] != 0 only for k >= j.  Independent of step 4:
+    //     enqueued on this depth's low-priority side stream so it fills the SMs the recursion
+    //     into A22 (small kernels, leaves) leaves idle.  L21 is read from the matrix (the W1
+    //     workspace is reused by the recursion); W2 has one region per depth.
+    double* W2 = h->dW2 + h->w2off[depth];
+    const long long sW2 = w2slab(h);
+    const bool ovl = h->opt_overlap && depth < MAX_DEPTH;
+    cudaStream_t s5a = ovl ? h->sideSt[depth] : h->st;
+    if (ovl) {
+        CUDA_TRY(cudaEventRecord(h->evA[depth], h->st));
+        CUDA_TRY(cudaStreamWaitEvent(s5a, h->evA[depth], 0));
+    }
     memset(&p, 0, sizeof(p));
     p.A = A21; p.lda = ld; p.sA = sA;
     p.B = Li11; p.ldb = ld; p.sB = sLi;
-    p.C = h->dW2; p.ldc = n1; p.sC = sW;
+    p.C = W2; p.ldc = n1; p.sC = sW2;
     p.mt = n2 / 128; p.nt = n1 / 128; p.K = n1; p.alpha = 1.0; p.beta = 0.0; p.kflags = GEMM_KJ_GE;
-    CUDA_TRY(gemm128(h, false, p, batch));
+    if (ovl) {
+        CUDA_TRY(gemm128_on(h, s5a, false, p, batch));
+        CUDA_TRY(cudaEventRecord(h->evB[depth], s5a));
+    }
+    // 4.
+    rc = potrf_inv_rec(h, A, Li, sA, sLi, dInfo, off + n1, n2, batch, depth + 1);
+    if (rc) return rc;
+    if (ovl) CUDA_TRY(cudaStreamWaitEvent(h->st, h->evB[depth], 0));
+    else CUDA_TRY(gemm128(h, false, p, batch));
     // 5b. Li21 = -Li22 * W2   A[i][k] = Li22[i][k] != 0 only for k <= i
     memset(&p, 0, sizeof(p));
     p.A = Li22; p.lda = ld; p.sA = sLi;
-    p.B = h->dW2; p.ldb = n1; p.sB = sW;
+    p.B = W2; p.ldb = n1; p.sB = sW2;
     p.C = Li21; p.ldc = ld; p.sC = sLi;
     p.mt = n2 / 128; p.nt = n1 / 128; p.K = n2; p.alpha = -1.0; p.beta = 0.0; p.kflags = GEMM_KI_LE;
     CUDA_TRY(gemm128(h, false, p, batch));
@@ -310,7 +337,11 @@ extern "C" int gpmpc_create(int N, int Nx, int Ny, int out_begin, int out_count,
     h->nloc_max = out_count; h->world = 1; h->rank = 0;
     h->Npad = (N + GPMPC_TILE - 1) / GPMPC_TILE * GPMPC_TILE;
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi));   // critical path first
+    }
     CUDA_TRY(cudaEventCreate(&h->ev0));
     CUDA_TRY(cudaEventCreate(&h->ev1));
     const long long np = h->Npad;
@@ -323,7 +354,24 @@ extern "C" int gpmpc_create(int N, int Nx, int Ny, int out_begin, int out_count,
     ALLOC(h->dL, out_count * slab(h));
     ALLOC(h->dLi, out_count * slab(h));
     ALLOC(h->dW1, out_count * wslab(h));
-    ALLOC(h->dW2, out_count * wslab(h));
+    {   // W2 workspace: one region per recursion depth (n_d = ceil(nb / 2^d) * 128 rows at depth d)
+        const int nb = h->Npad / 128;
+        long long off = 0;
+        for (int d = 0; d < MAX_DEPTH; ++d) {
+            h->w2off[d] = off;
+            const long long nd = (long long)((nb + (1 << d) - 1) >> d) * 128;
+            off += nd * nd / 4 + 128;
+        }
+        h->w2off[MAX_DEPTH] = off;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int d = 0; d < MAX_DEPTH; ++d) {
+            CUDA_TRY(cudaStreamCreateWithPriority(&h->sideSt[d], cudaStreamNonBlocking, lo));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->evA[d], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->evB[d], cudaEventDisableTiming));
+        }
+    }
+    ALLOC(h->dW2, out_count * w2slab(h));
     ALLOC(h->dAlpha, (long long)out_count * np);
     ALLOC(h->dTmp, (long long)out_count * np);
     ALLOC(h->dRes, 2 * out_count);
@@ -353,6 +401,11 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
     if (h->hPinned) cudaFreeHost(h->hPinned);
+    for (int d = 0; d < MAX_DEPTH; ++d) {
+        if (h->sideSt[d]) { cudaStreamSynchronize(h->sideSt[d]); cudaStreamDestroy(h->sideSt[d]); }
+        if (h->evA[d]) cudaEventDestroy(h->evA[d]);
+        if (h->evB[d]) cudaEventDestroy(h->evB[d]);
+    }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->st) cudaStreamDestroy(h->st);
@@ -596,6 +649,7 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
     }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "tri_variant")) { h->opt_tri_variant = (int)value; return GPMPC_OK; }
+    if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "peer")) { h->opt_peer = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "leaf_variant")) { h->opt_leaf_variant = (int)value; return GPMPC_OK; }
     set_error(h, "unknown option %s", name);

@@ -311,8 +311,11 @@ def _maha(a1, b1, Q1):
             - 2 * aQ @ b1.T)
 
 
-def gp_exact_moment(invK, X, Y, hyper, inputmean, inputcov):
+def gp_exact_moment(invK, X, Y, hyper, inputmean, inputcov, extended=False):
     """``gp_exact_moment`` ``gp_functions.py:344-418``, one test point.
+
+    ``extended=True`` evaluates the N x N sums (which cancel ~6-7 digits: beta beta^T vs
+    invK) in numpy longdouble -- a higher-precision yardstick for judging fp64 noise.
 
     Quirks kept: hyper=log(hyper) then exponentiated (:367); det through the
     product of the QR diagonal (:378-380) -- restated with slogdet's value
@@ -352,8 +355,18 @@ def gp_exact_moment(invK, X, Y, hyper, inputmean, inputcov):
             R = inputcov @ np.diag(np.exp(-2 * lh[a, :Nx]) + np.exp(-2 * lh[b, :Nx])) + eye
             t = 1.0 / np.sqrt(det(R))
             ij = v / np.exp(2 * lh[b, :Nx])[None, :]
-            Q = np.exp(log_k[:, a][:, None] + log_k[:, b][None, :]
-                       + _maha(ii, -ij, np.linalg.solve(R, inputcov * 0.5)))
+            Qm = np.linalg.solve(R, inputcov * 0.5)
+            if extended:
+                ld = np.longdouble
+                Q = np.exp(log_k[:, a].astype(ld)[:, None] + log_k[:, b].astype(ld)[None, :]
+                           + _maha(ii.astype(ld), -ij.astype(ld), Qm.astype(ld)))
+                A = np.outer(beta[:, a].astype(ld), beta[:, b].astype(ld))
+                if b == a:
+                    A = A - np.asarray(invK[a]).astype(ld)
+                covariance[a, b] = float(t * np.sum(A * Q))
+                covariance[b, a] = covariance[a, b]
+                continue
+            Q = np.exp(log_k[:, a][:, None] + log_k[:, b][None, :] + _maha(ii, -ij, Qm))
             A = np.outer(beta[:, a], beta[:, b])
             if b == a:
                 A = A - invK[a]

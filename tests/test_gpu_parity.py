@@ -225,8 +225,13 @@ def test_exact_moment_matching_vs_restatement():
     mean, var, cov, _ = eng.predict(Z, Sg, L.METHOD_EM, want_jac=False)
     for h in range(5):
         mo, co = orc.gp_exact_moment(invK, m['X'], m['Y'], m['hyper'], Z[h], Sg[h])
+        _, cx = orc.gp_exact_moment(invK, m['X'], m['Y'], m['hyper'], Z[h], Sg[h], extended=True)
         assert relinf(mean[h], mo) < TOL
-        assert relinf(cov[h], co) < TOL
+        # the fp64 numpy restatement itself sits ~1e-5..1e-4 from the extended-precision sum
+        # (cancellation of beta beta^T against invK); the GPU must be at least as close
+        noise = relinf(co, cx)
+        assert relinf(cov[h], cx) < max(3 * noise, 1e-6), (relinf(cov[h], cx), noise)
+        assert relinf(cov[h], co) < 5e-4
         assert np.array_equal(var[h], np.diag(cov[h]))
     # EM -> ME as the input covariance vanishes (mean exactly, variance up to the invK cancellation)
     mean0, _, cov0, _ = eng.predict(Z, 1e-14 * np.eye(6), L.METHOD_EM, want_jac=False)
