@@ -79,3 +79,13 @@ def test_bounds_and_init_follow_the_reference():
     assert [count_mean_params(m, 4) for m in ('zero', 'const', 'linear', 'polynomial')] == [0, 1, 5, 9]
     with pytest.raises(NameError):
         count_mean_params('cubic', 4)
+
+
+def test_bench_workload_generator_matches_the_oracle_generator():
+    import bench
+    from oracle import gp_oracle as orc
+    a = bench.make_workload(50, 4, 2, 3, 7)
+    b = orc.synthetic_problem(50, 4, 2, config_id=3, H=7)
+    for k in ('X', 'Y', 'hyper', 'Z', 'Sigma'):
+        assert np.array_equal(a[k], b[k])
+    assert set(bench.WORKLOADS) == {'c2', 'c3', 'c5'}

@@ -375,3 +375,64 @@ def test_gp_class_trains_like_the_reference_driver():
         assert orc.calc_NLL(hy_fd[a], Xs, Ys[:, a]) == pytest.approx(
             orc.calc_NLL(ref['hyper'][a], Xs, Ys[:, a]), rel=1e-4, abs=1e-3)
     gp.close(); gp_fd.close()
+
+
+# ------------------------------------------------------------------ edge cases / error behaviour
+@pytest.mark.parametrize('N,Nx,Ny,H', [(1, 1, 1, 1), (2, 3, 2, 5), (127, 4, 1, 64), (128, 4, 1, 65), (129, 2, 2, 129),
+                                       (257, 32, 1, 3)])
+def test_edge_sizes(N, Nx, Ny, H):
+    """smallest / ragged / maximum-Nx shapes: padding to 128, H chunking at 64, Nx = NX_MAX."""
+    rng = np.random.default_rng(N * 7 + H)
+    X = rng.standard_normal((N, Nx)); Y = rng.standard_normal((N, Ny))
+    hyper = np.column_stack([rng.uniform(1.0, 3.0, (Ny, Nx)), np.full(Ny, 1.3), np.full(Ny, 0.05)])
+    Z = rng.standard_normal((H, Nx)); A = rng.standard_normal((Nx, Nx)); Sig = 1e-3 * (np.eye(Nx) + 0.1 * A @ A.T)
+    post = orc.postfit(X, Y, hyper, lapack_general_solve=False)
+    mo, vo = orc.gp_mean_var(X, hyper, post['alpha'], post['chol'], Z)
+    Jo = orc.gp_mean_jac(X, hyper, post['alpha'], Z); co = orc.ta_cov(vo, Jo, Sig)
+    eng, info = _fit_engine(X, Y, hyper)
+    mean, var, cov, jac = eng.predict(Z, Sig, _L().METHOD_TA)
+    assert relinf(mean, mo) < TOL and relinf(var, vo) < TOL and relinf(cov, co) < TOL and relinf(jac, Jo) < TOL
+    assert relinf(eng.get(_L().GET_CHOL, Ny - 1), post['chol'][Ny - 1]) < 1e-10
+    pc = eng.posterior_cov(Z[:min(H, 7)])
+    ks = orc.covSEard(X, Z[:min(H, 7)], hyper[0, :Nx], hyper[0, Nx] ** 2)
+    v = np.linalg.solve(post['chol'][0], ks)
+    assert relinf(pc[0], hyper[0, Nx] ** 2 - v.T @ v) < TOL
+    eng.close()
+
+
+def test_argument_errors_fail_loudly():
+    import gp_mpc_b200
+    L = _L()
+    with pytest.raises(L.GpmpcError):
+        gp_mpc_b200.Engine(10, 33, 1, device=0)                  # Nx above NX_MAX
+    with pytest.raises(L.GpmpcError):
+        gp_mpc_b200.Engine(10, 2, 2, out_begin=1, out_count=2, device=0)
+    eng = gp_mpc_b200.Engine(10, 2, 1, device=0)
+    with pytest.raises(L.GpmpcError):
+        eng.factorize()                                          # no data / hyper yet
+    rng = np.random.default_rng(0)
+    eng.set_data(rng.standard_normal((10, 2)), rng.standard_normal((10, 1)))
+    with pytest.raises(L.GpmpcError):
+        eng.set_hyper(np.array([[0.0, 1.0, 1.0, 0.1]]))          # zero length scale
+    eng.set_hyper(np.array([[1.0, 1.0, 1.0, 0.1]]))
+    with pytest.raises(L.GpmpcError):
+        eng.predict(np.zeros((1, 2)))                            # not factorised
+    eng.factorize()
+    with pytest.raises(L.GpmpcError):
+        eng.get(L.GET_CHOL, 3)                                   # output not owned
+    with pytest.raises(L.GpmpcError):
+        eng.set_option('no_such_option', 1)
+    with pytest.raises(L.GpmpcError):
+        eng.predict(np.zeros((2, 2)), None, L.METHOD_EM, want_jac=False)     # EM needs Sigma
+    eng.close()
+    gp = gp_mpc_b200.GP(rng.standard_normal((12, 3)), rng.standard_normal((12, 2)), normalize=False,
+                        hyper=dict(hyper=np.array([[1., 1., 1., 1., .1], [1., 2., 1., 1., .1]])))
+    with pytest.raises(NotImplementedError):
+        gp.set_method('old_TA')
+    with pytest.raises(NotImplementedError):
+        gp.update_data(np.zeros((1, 3)), np.zeros((1, 2)))
+    gp.update_data_all(rng.standard_normal((4, 3)), rng.standard_normal((4, 2)))
+    assert gp.get_size() == (16, 2, 1)
+    gp.replace_data_all(rng.standard_normal((5, 3)), rng.standard_normal((5, 2)))
+    assert gp.get_size() == (5, 2, 1)
+    gp.close()
