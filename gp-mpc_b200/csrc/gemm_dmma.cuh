@@ -48,7 +48,9 @@ struct GemmSmem {
     static constexpr int BYTES = STAGES * (A_STAGE + B_STAGE) * 8;
 };
 
-template <int BM, int BN, int WM, int WN, bool BT, int STAGES, int MINB>
+// TMA = true: tile rows are fetched with 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) that
+// complete on one mbarrier per stage instead of cp.async groups; same smem layout and compute.
+template <int BM, int BN, int WM, int WN, bool BT, int STAGES, int MINB, bool TMA = false>
 __global__ void __launch_bounds__(WM * WN * 32, MINB)
 gemm_dmma_kernel(const GemmParams p)
 {
@@ -63,6 +65,8 @@ gemm_dmma_kernel(const GemmParams p)
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));   // TMA only
+    constexpr uint32_t STAGE_TX = BT ? (BM + BN) * BK * 8 : (BM * BK + BK * BN) * 8;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -111,22 +115,29 @@ gemm_dmma_kernel(const GemmParams p)
     auto load_stage = [&](int s, int k0) {
         double* as = As + s * A_STAGE;
         double* bs = Bs + s * B_STAGE;
-#pragma unroll
-        for (int c = tid; c < BM * 8; c += NT) {
-            const int r = c >> 3, ch = c & 7;
-            cp_async16(as + r * LDA_S + ch * 2, Ag + (long long)r * p.lda + k0 + ch * 2);
-        }
-        if (BT) {
-#pragma unroll
-            for (int c = tid; c < BN * 8; c += NT) {
-                const int r = c >> 3, ch = c & 7;
-                cp_async16(bs + r * LDB_S + ch * 2, Bg + (long long)r * p.ldb + k0 + ch * 2);
-            }
+        if constexpr (TMA) {
+            if (tid == 0) mbar_arrive_expect_tx(full + s, STAGE_TX);
+            for (int r = tid; r < BM; r += NT) tma_bulk_g2s(as + r * LDA_S, Ag + (long long)r * p.lda + k0, BK * 8, full + s);
+            if (BT) { for (int r = tid; r < BN; r += NT) tma_bulk_g2s(bs + r * LDB_S, Bg + (long long)r * p.ldb + k0, BK * 8, full + s); }
+            else { for (int r = tid; r < BK; r += NT) tma_bulk_g2s(bs + r * LDB_S, Bg + (long long)(k0 + r) * p.ldb, BN * 8, full + s); }
         } else {
 #pragma unroll
-            for (int c = tid; c < BK * (BN / 2); c += NT) {
-                const int r = c / (BN / 2), ch = c % (BN / 2);
-                cp_async16(bs + r * LDB_S + ch * 2, Bg + (long long)(k0 + r) * p.ldb + ch * 2);
+            for (int c = tid; c < BM * 8; c += NT) {
+                const int r = c >> 3, ch = c & 7;
+                cp_async16(as + r * LDA_S + ch * 2, Ag + (long long)r * p.lda + k0 + ch * 2);
+            }
+            if (BT) {
+#pragma unroll
+                for (int c = tid; c < BN * 8; c += NT) {
+                    const int r = c >> 3, ch = c & 7;
+                    cp_async16(bs + r * LDB_S + ch * 2, Bg + (long long)r * p.ldb + k0 + ch * 2);
+                }
+            } else {
+#pragma unroll
+                for (int c = tid; c < BK * (BN / 2); c += NT) {
+                    const int r = c / (BN / 2), ch = c % (BN / 2);
+                    cp_async16(bs + r * LDB_S + ch * 2, Bg + (long long)(k0 + r) * p.ldb + ch * 2);
+                }
             }
         }
     };
@@ -137,19 +148,28 @@ gemm_dmma_kernel(const GemmParams p)
 #pragma unroll
         for (int ni = 0; ni < NF; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
 
+    if (TMA) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) load_stage(s, k_lo + s * BK);
-        cp_async_commit();
+        if (!TMA) cp_async_commit();
     }
 
     for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<STAGES - 2>();
+        if (TMA) mbar_wait(full + kt % STAGES, (kt / STAGES) & 1);
+        else cp_async_wait<STAGES - 2>();
         __syncthreads();
         {   // prefetch the stage that was consumed in the previous iteration
             const int kn = kt + STAGES - 1;
             if (kn < nk) load_stage(kn % STAGES, k_lo + kn * BK);
-            cp_async_commit();
+            if (!TMA) cp_async_commit();
         }
         const int s = kt % STAGES;
         const double* as = As + s * A_STAGE + (wm * WTM + g) * LDA_S + t;
@@ -170,7 +190,7 @@ gemm_dmma_kernel(const GemmParams p)
                     dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
     }
-    cp_async_wait<0>();
+    if (!TMA) cp_async_wait<0>();
 
     // epilogue: each lane owns two adjacent columns of every 8x8 fragment -> 16-byte accesses
     double* Cg = p.C + bz * p.sC + part_off;
@@ -198,14 +218,15 @@ gemm_dmma_kernel(const GemmParams p)
     }
 }
 
-template <int BM, int BN, int WM, int WN, bool BT, int STAGES, int MINB>
+template <int BM, int BN, int WM, int WN, bool BT, int STAGES, int MINB, bool TMA = false>
 static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cudaStream_t st)
 {
     using SM = GemmSmem<BM, BN, BT, STAGES>;
-    auto kern = gemm_dmma_kernel<BM, BN, WM, WN, BT, STAGES, MINB>;
+    auto kern = gemm_dmma_kernel<BM, BN, WM, WN, BT, STAGES, MINB, TMA>;
+    constexpr int BYTES = SM::BYTES + (TMA ? STAGES * 8 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -213,6 +234,6 @@ static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cuda
     const int tiles = p.lower ? R * p.mt * (p.mt + 1) / 2 : p.mt * p.nt;
     dim3 grid(tiles, p.ksplit ? nchunks : 1, batch);
     if (p.lpt) grid = dim3(batch, p.nt, p.ksplit ? nchunks : 1);      // requires mt == 1
-    kern<<<grid, WM * WN * 32, SM::BYTES, st>>>(p);
+    kern<<<grid, WM * WN * 32, BYTES, st>>>(p);
     return cudaGetLastError();
 }
