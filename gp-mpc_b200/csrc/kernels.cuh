@@ -319,33 +319,40 @@ leaf_potrf_trtri_kernel(double* __restrict__ A, int lda, long long sA,
 
 __device__ __forceinline__ void warp_potrf16_trtri16(double* D, double* Dinv, int* info, int info_val0, int lane)
 {
-    // D: 16x16 block (lower part valid) with row stride LF_LD; Dinv: [16][17]
-    const int r = lane & 15, hf = lane >> 4;
+    // D: 16x16 block (lower part valid) with row stride LF_LD; Dinv: [16][17].
+    // Register-resident: lane r (and its mirror r+16) holds row r; pivots / multipliers travel
+    // by shuffle, so the 16 column steps need no shared-memory round trips.
+    const unsigned full = 0xffffffffu;
+    const int r = lane & 15;
+    double a[16], ipd[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = D[r * LF_LD + k];
+#pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const double d = D[j * LF_LD + j];
+        const double d = __shfl_sync(full, a[j], j);
         if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, info_val0 + j + 1);
-        const double pv = sqrt(d), ip = 1.0 / pv;
-        __syncwarp();
-        if (lane == j) D[j * LF_LD + j] = pv;
-        else if (lane > j && lane < 16) D[lane * LF_LD + j] *= ip;
-        __syncwarp();
-        if (r > j) {
-            const double lrj = D[r * LF_LD + j];
-            for (int k = j + 1 + hf; k <= r; k += 2) D[r * LF_LD + k] = fma(-lrj, D[k * LF_LD + j], D[r * LF_LD + k]);
+        const double pv = sqrt(d);
+        ipd[j] = 1.0 / pv;
+        a[j] = (r == j) ? pv : a[j] * ipd[j];              // l_rj for r > j (LAPACK dpotf2 scales by 1/ajj too)
+#pragma unroll
+        for (int k = j + 1; k < 16; ++k) {
+            const double lkj = __shfl_sync(full, a[j], k);
+            a[k] = fma(-a[j], lkj, a[k]);                  // meaningful for r >= k; upper part is never read
         }
-        __syncwarp();
     }
-    if (lane < 16) {       // column `lane` of the inverse by forward substitution, x kept in registers
-        double x[16];
+    if (lane < 16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            double sacc = 0.0;
+        for (int k = 0; k < 16; ++k) if (k <= r) D[r * LF_LD + k] = a[k];
+    }
+    // column r of the inverse by forward substitution; L[i][k] is broadcast from lane i
+    double x[16];
 #pragma unroll
-            for (int k = 0; k < i; ++k) sacc = fma(D[i * LF_LD + k], x[k], sacc);
-            const double idg = 1.0 / D[i * LF_LD + i];
-            x[i] = (i < lane) ? 0.0 : ((i == lane) ? idg : -sacc * idg);
-            Dinv[i * 17 + lane] = x[i];
-        }
+    for (int i = 0; i < 16; ++i) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) sacc = fma(__shfl_sync(full, a[k], i), x[k], sacc);
+        x[i] = (i < r) ? 0.0 : ((i == r) ? ipd[i] : -sacc * ipd[i]);
+        if (lane < 16) Dinv[i * 17 + r] = x[i];
     }
     __syncwarp();
 }
