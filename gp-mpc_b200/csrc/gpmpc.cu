@@ -739,6 +739,17 @@ static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm
     return cudaGetLastError();
 }
 
+static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
+{
+    const int Nx = h->Nx;       // register-array extent NXP: next multiple of 4 up to 16, then 24 / 32
+    if (Nx <= 4) return launch_ks<4>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 8) return launch_ks<8>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 12) return launch_ks<12>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 16) return launch_ks<16>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 24) return launch_ks<24>(h, dZc, Hc, bm, nblk);
+    return launch_ks<32>(h, dZc, Hc, bm, nblk);
+}
+
 // C = alpha * A(h-major rows) * T^T (+ Cin) with T = Li or L (lower), reduced over split-K
 // into `Vout` (may be null) and squared-norm partials into dSQ when sq != 0
 static int tri_product(gpmpc_handle_t h, const double* Amat, const double* T, int bm, int Hc, int ksplit,
@@ -798,9 +809,7 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
         const int Hc = std::min(HB, H - h0);
         const int bm = (Hc + 7) / 8 * 8;
         const double* dZc = dZ + (long long)h0 * Nx;
-        cudaError_t e = (Nx <= 8) ? launch_ks<8>(h, dZc, Hc, bm, nblk_mj)
-                      : (Nx <= 16) ? launch_ks<16>(h, dZc, Hc, bm, nblk_mj) : launch_ks<32>(h, dZc, Hc, bm, nblk_mj);
-        CUDA_TRY(e);
+        CUDA_TRY(launch_ks_any(h, dZc, Hc, bm, nblk_mj));
         if (!h->opt_refine) {
             int rc = tri_product(h, h->dKST, h->dLi, bm, Hc, ksplit, nullptr);
             if (rc) return rc;
@@ -1082,8 +1091,7 @@ extern "C" int gpmpc_posterior_cov(gpmpc_handle_t h, int H, const double* Z, dou
     for (int h0 = 0; h0 < H && rc == GPMPC_OK; h0 += HB) {
         const int Hc = std::min(HB, H - h0), bm = (Hc + 7) / 8 * 8;
         const double* dZc = h->dZ + (long long)h0 * Nx;
-        cudaError_t e = (Nx <= 8) ? launch_ks<8>(h, dZc, Hc, bm, nblk_mj)
-                      : (Nx <= 16) ? launch_ks<16>(h, dZc, Hc, bm, nblk_mj) : launch_ks<32>(h, dZc, Hc, bm, nblk_mj);
+        cudaError_t e = launch_ks_any(h, dZc, Hc, bm, nblk_mj);
         if (e != cudaSuccess) { set_error(h, "posterior_cov ks: %s", cudaGetErrorString(e)); rc = GPMPC_ERR_CUDA; break; }
         rc = tri_product(h, h->dKST, h->dLi, bm, Hc, ksplit, h->dV);
         if (rc) break;

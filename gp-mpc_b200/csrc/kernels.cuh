@@ -7,98 +7,13 @@
 #define KB_TILE 64
 
 // ---------------------------------------------------------------------------------------
-// a1/a2  K = sf2 * exp(-1/2 sum_d ((x_id - x_jd)/ell_d)^2) + (sn2 + jitter) I
-//   gp_functions.py:17-22 (direct differences), optimize.py:342-344 (noise + symmetrise:
-//   the direct-difference form is exactly symmetric, so (K+K^T)/2 is the identity map).
-//   XT is the d-major copy of X: XT[d*ldx + i].  One CTA computes one 64x64 tile of the
-//   lower triangle and (full mode) also stores its transpose through shared memory, so
-//   each exp is evaluated once for two outputs.  Rows/cols >= N get the identity tail.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-kbuild_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
-              const double* __restrict__ hyp, int hyp_ld, const double* __restrict__ jitter,
-              double* __restrict__ K, int ld, long long sK, int full)
-{
-    extern __shared__ double sm[];
-    double* Xi = sm;                       // [Nx][64] scaled by 1/ell
-    double* Xj = sm + Nx * KB_TILE;        // [Nx][64]
-    double* T = sm + 2 * Nx * KB_TILE;     // [64][65] transpose staging
-
-    const int a = blockIdx.z;
-    const double* hp = hyp + (long long)a * hyp_ld;
-    const int tt = blockIdx.x;
-    int bi = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
-    while (bi * (bi + 1) / 2 > tt) --bi;
-    while ((bi + 1) * (bi + 2) / 2 <= tt) ++bi;
-    const int bj = tt - bi * (bi + 1) / 2;
-    const int i0 = bi * KB_TILE, j0 = bj * KB_TILE;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-
-    for (int idx = tid; idx < Nx * KB_TILE; idx += 256) {
-        const int d = idx / KB_TILE, r = idx % KB_TILE;
-        const double inv = 1.0 / hp[d];
-        Xi[idx] = XT[(long long)d * ldx + i0 + r] * inv;
-        Xj[idx] = XT[(long long)d * ldx + j0 + r] * inv;
-    }
-    __syncthreads();
-
-    double acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-    for (int d = 0; d < Nx; ++d) {
-        double xi[4], xj[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) xi[r] = Xi[d * KB_TILE + ty + 16 * r];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) xj[c] = Xj[d * KB_TILE + tx + 16 * c];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { const double df = xi[r] - xj[c]; acc[r][c] = fma(df, df, acc[r][c]); }
-    }
-    const double sf2 = hp[Nx] * hp[Nx];
-    const double dg = hp[Nx + 1] * hp[Nx + 1] + (jitter ? jitter[a] : 0.0);
-    double* Ka = K + (long long)a * sK;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int row = i0 + ty + 16 * r;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int col = j0 + tx + 16 * c;
-            double v;
-            if (row < N && col < N) {
-                v = sf2 * exp(-0.5 * acc[r][c]);
-                if (row == col) v += dg;
-            } else {
-                v = (row == col) ? 1.0 : 0.0;
-            }
-            acc[r][c] = v;
-            Ka[(long long)row * ld + col] = v;
-        }
-    }
-    if (full && bi != bj) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) T[(tx + 16 * c) * (KB_TILE + 1) + ty + 16 * r] = acc[r][c];
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                Ka[(long long)(j0 + ty + 16 * r) * ld + i0 + tx + 16 * c] = T[(ty + 16 * r) * (KB_TILE + 1) + tx + 16 * c];
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// a1/a2 (v2)  K build with the pairwise distances on the fp64 TENSOR pipe.
+// a1/a2  K = sf2 exp(-1/2 sum_d ((x_id - x_jd)/ell_d)^2) + (sn2 + jitter) I   (gp_functions.py:17-22,
+//   optimize.py:303-319, :342-344), with the pairwise distances on the fp64 TENSOR pipe.
 //   With u_i = sqrt(log2 e) (x_i - mu)/ell and q_i = -1/2 |u_i|^2 + 1/2 log2 sf2,
 //       log2 k(x_i, x_j) = q_i + q_j + u_i . u_j            (= log2 sf2 - log2(e)/2 |xs_i - xs_j|^2)
 //   so the O(N^2 Nx) part is a rank-Nx product done with DMMA m8n8k4 (tensor pipe), leaving the
 //   fp64 pipe only ~14 instructions per pair (two adds, clamp, a 16-entry-table exp2 with a
-//   degree-7 polynomial).  ncu on the v1 kernel showed the fp64 pipe 48 % busy and DRAM 41 %:
+//   degree-7 polynomial).  ncu on the first (direct-difference, libm exp) kernel showed the fp64 pipe 48 % busy and DRAM 41 %:
 //   the two pipes now overlap and the kernel becomes write-bandwidth bound.
 //   The kernel is translation invariant, so inputs are centred on the column means mu: the
 //   expansion's cancellation error is eps*|u|^2 with |u| measured from the data centre
@@ -584,7 +499,7 @@ logdet_dot_kernel(const double* __restrict__ L, int ld, long long sL,
 //   KST[a][h][i] (h-major) is the B^T operand of the v = Linv ks tensor-core product.
 //   grid (Npad/1024, BM rows, outputs); rows h >= H are zero-filled.
 // ---------------------------------------------------------------------------------------
-#define KS_CHUNK 1024
+#define KS_CHUNK 2048
 template <int NXP>
 __global__ void __launch_bounds__(256)
 ks_mean_jac_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,

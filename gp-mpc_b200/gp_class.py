@@ -289,6 +289,38 @@ class GP:
                                      None if cov is None else np.asarray(cov, dtype=np.float64))
         return mean.reshape(self.__Ny, 1), c[0]
 
+    def rollout(self, x0, u, methods=None):
+        """ The numeric multi-step prediction of ``predict_compare`` (reference
+        gp_class.py:746-804, open-loop branch) without the plotting / plant simulation:
+        for every method, propagate (mean, covariance) through ``predict`` over the input
+        sequence u:(Nt,Nu), starting from x0 with covariance diag(sn2) (+1e-6 on the inputs).
+        Returns mean, var of shape (len(methods), Nt+1, Ny); var is rescaled by stdY^2 when
+        normalize (:795-796)."""
+        Nx, Ny = self.__Nx, self.__Ny
+        u = np.asarray(u, dtype=np.float64).reshape(-1, self.__Nu)
+        Nt = u.shape[0]
+        initVar = self.__hyper[:, Nx + 1] ** 2
+        methods = ['EM', 'TA', 'ME'] if methods is None else list(methods)
+        mean = np.zeros((len(methods), Nt + 1, Ny))
+        var = np.zeros((len(methods), Nt + 1, Ny))
+        covar = np.eye(Nx) * 1e-6                       # shared across methods, as in the reference
+        keep = self.__gp_method
+        for i, meth in enumerate(methods):
+            self.set_method(meth)
+            mean_t = np.asarray(x0, dtype=np.float64).reshape(-1)
+            covar[:Ny, :Ny] = np.diag(initVar)
+            mean[i, 0, :] = mean_t
+            for t in range(1, Nt + 1):
+                mean_t, covar_x = self.predict(mean_t, u[t - 1, :], covar)
+                mean_t = np.array(mean_t).reshape(Ny)
+                mean[i, t, :] = mean_t
+                var[i, t, :] = np.diag(covar_x)
+                if self.__normalize:
+                    var[i, t, :] = self.inverse_variance(var[i, t, :])
+                covar[:Ny, :Ny] = covar_x
+        self.set_method(keep)
+        return mean, var
+
     def get_size(self):
         """ (N, Ny, Nu)  (reference gp_class.py:266-274) """
         return self.__N, self.__Ny, self.__Nu
@@ -496,6 +528,30 @@ class GP:
         output_dict = self._GP__to_dict()
         with open(filename + ".json", "w") as outfile:
             json.dump(output_dict, outfile)
+
+    def save_model_npz(self, filename):
+        """ Binary side-car of save_model for large N (a 16384^2 factor is ~5 GB as JSON text):
+        same fields, one compressed .npz; chol / invK are NOT stored (they are recomputed on the
+        GPU at load time, as load_model does anyway). """
+        d = dict(X=self.__X, Y=self.__Y, hyper=self.__hyper, mean_func=np.array(self.__mean_func),
+                 normalize=np.array(bool(self.__normalize)))
+        if self.__normalize:
+            d.update(xlb=np.asarray(self.__xlb, dtype=np.float64), xub=np.asarray(self.__xub, dtype=np.float64),
+                     ulb=np.asarray(self.__ulb, dtype=np.float64), uub=np.asarray(self.__uub, dtype=np.float64),
+                     meanY=self.__meanY, stdY=self.__stdY, meanZ=self.__meanZ, stdZ=self.__stdZ,
+                     meanX=self.__meanX, stdX=self.__stdX, meanU=self.__meanU, stdU=self.__stdU)
+        np.savez_compressed(filename + '.npz', **d)
+
+    @classmethod
+    def load_model_npz(cls, filename, **kwargs):
+        z = np.load(filename + '.npz')
+        kw = dict(X=z['X'], Y=z['Y'], hyper=dict(hyper=z['hyper']), mean_func=str(z['mean_func']),
+                  normalize=bool(z['normalize']))
+        if kw['normalize']:
+            kw.update(xlb=z['xlb'], xub=z['xub'], ulb=z['ulb'], uub=z['uub'],
+                      meta={k: z[k] for k in ('meanY', 'stdY', 'meanZ', 'stdZ', 'meanX', 'stdX', 'meanU', 'stdU')})
+        kw.update(kwargs)
+        return cls(**kw)
 
     @classmethod
     def load_model(cls, filename, **kwargs):

@@ -327,12 +327,27 @@ def test_gp_class_validate_and_io(tmp_path):
     m1, c1 = gp.predict(d['x0'], d['u0'], d['Sigma'])
     m2, c2 = gp2.predict(d['x0'], d['u0'], d['Sigma'])
     assert np.array_equal(m1, m2) and np.array_equal(c1, c2)
+    gp.save_model_npz(path)
+    gp3 = gp_mpc_b200.GP.load_model_npz(path)
+    m3, c3 = gp3.predict(d['x0'], d['u0'], d['Sigma'])
+    assert np.array_equal(m1, m3) and np.array_equal(c1, c3)
+    gp3.close()
     # batched horizon call == per-point calls
     xs = np.tile(d['x0'], (5, 1)) * (1 + 0.01 * np.arange(5)[:, None]); us = np.tile(d['u0'], (5, 1))
     mb, cb = gp.predict_batch(xs, us, d['Sigma'])
     for h in range(5):
         mh, ch = gp.predict(xs[h], us[h], d['Sigma'])
         assert relinf(mb[h], mh.ravel()) < 1e-12 and relinf(cb[h], ch) < 1e-12
+    # sequential roll-out (numeric part of predict_compare, gp_class.py:777-804) vs the oracle loop
+    useq = np.tile(d['u0'], (6, 1)) * (1 + 0.02 * np.arange(6)[:, None])
+    rm, rv = gp.rollout(d['x0'], useq, methods=['TA', 'ME'])
+    for i, meth in enumerate(['TA', 'ME']):
+        cv = np.eye(6) * 1e-6; cv[:4, :4] = np.diag(m['hyper'][:, 7] ** 2); xt = d['x0'].copy()
+        for t in range(6):
+            mo_, co_ = orc.predict(m, xt, useq[t], cv, meth)
+            xt = mo_.ravel(); cv[:4, :4] = co_
+            assert relinf(rm[i, t + 1], xt) < TOL
+            assert relinf(rv[i, t + 1], np.diag(co_) * m['meta']['stdY'] ** 2) < 1e-5
     # kernel helper keeps the reference's error behaviour
     with pytest.raises(ValueError):
         gp.covSEard(np.zeros((3, 6)), np.zeros((2, 5)), np.ones(6), 1.0)
