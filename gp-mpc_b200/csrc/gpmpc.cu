@@ -671,7 +671,7 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
     if (!h->dKST) {
         ALLOC(h->dKST, (long long)h->nloc * HB * np);
         ALLOC(h->dPart, (long long)h->nloc * MAX_CHUNKS * HB * np);
-        ALLOC(h->dPMJ, (long long)h->nloc * HB * ((np + KS_CHUNK - 1) / KS_CHUNK) * (h->Nx + 1));
+        ALLOC(h->dPMJ, (long long)h->nloc * HB * ((np + 1023) / 1024) * (h->Nx + 1));
         ALLOC(h->dSQ, (long long)h->nloc * HB * ((np + 255) / 256));
     }
     if (h->opt_refine && !h->dV) {
@@ -730,12 +730,18 @@ static cudaError_t trigemm_launch(int variant, int bm, const GemmParams& p, int 
     }
 }
 
+static inline int ks_chunk(gpmpc_handle_t h) { return h->Npad <= 4096 ? 1024 : KS_CHUNK; }
+
 template <int NXP>
 static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
     dim3 g(nblk, bm, h->nloc);
-    ks_mean_jac_kernel<NXP><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
-                                                   dZc, Hc, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
+    if (ks_chunk(h) == 1024)
+        ks_mean_jac_kernel<NXP, 1024><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
+                                                             dZc, Hc, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
+    else
+        ks_mean_jac_kernel<NXP, KS_CHUNK><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
+                                                                 dZc, Hc, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
     return cudaGetLastError();
 }
 
@@ -789,7 +795,7 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
 {
     const int np = h->Npad, Nx = h->Nx;
     const int ksplit = choose_ksplit(h);
-    const int nblk_mj = (np + KS_CHUNK - 1) / KS_CHUNK, nblk_sq = (np + 255) / 256;
+    const int nblk_mj = (np + ks_chunk(h) - 1) / ks_chunk(h), nblk_sq = (np + 255) / 256;
     // fused epilogue + all-gather over peer memory when the exchange block is attached
     const int use_peers = (h->world > 1 && h->peer_ready && h->opt_peer && H <= h->peerHcap) ? 1 : 0;
     PeerArgs pa;
@@ -1087,7 +1093,7 @@ extern "C" int gpmpc_posterior_cov(gpmpc_handle_t h, int H, const double* Z, dou
     if (!h->dV) { ALLOC(h->dV, (long long)nl * HB * np); ALLOC(h->dR, (long long)nl * HB * np); }
     CUDA_TRY(cudaMemcpyAsync(h->dZ, Z, (size_t)H * Nx * 8, cudaMemcpyHostToDevice, h->st));
     const int ksplit = choose_ksplit(h);
-    const int nblk_mj = (np + KS_CHUNK - 1) / KS_CHUNK;
+    const int nblk_mj = (np + ks_chunk(h) - 1) / ks_chunk(h);
     for (int h0 = 0; h0 < H && rc == GPMPC_OK; h0 += HB) {
         const int Hc = std::min(HB, H - h0), bm = (Hc + 7) / 8 * 8;
         const double* dZc = h->dZ + (long long)h0 * Nx;

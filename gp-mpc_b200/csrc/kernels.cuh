@@ -499,8 +499,8 @@ logdet_dot_kernel(const double* __restrict__ L, int ld, long long sL,
 //   KST[a][h][i] (h-major) is the B^T operand of the v = Linv ks tensor-core product.
 //   grid (Npad/1024, BM rows, outputs); rows h >= H are zero-filled.
 // ---------------------------------------------------------------------------------------
-#define KS_CHUNK 2048
-template <int NXP>
+#define KS_CHUNK 2048          // points per CTA for large N (1024 when Npad <= 4096: more CTAs)
+template <int NXP, int CH>
 __global__ void __launch_bounds__(256)
 ks_mean_jac_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
                    const double* __restrict__ hyp, int hyp_ld,
@@ -515,8 +515,8 @@ ks_mean_jac_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
     const int tid = threadIdx.x;
     double* krow = KST + (long long)a * sK + (long long)h * ldk;
     if (h >= H) {
-        for (int q = 0; q < KS_CHUNK / 256; ++q) {
-            const int i = blk * KS_CHUNK + tid + 256 * q;
+        for (int q = 0; q < CH / 256; ++q) {
+            const int i = blk * CH + tid + 256 * q;
             if (i < ldk) krow[i] = 0.0;
         }
         return;
@@ -534,8 +534,8 @@ ks_mean_jac_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
 #pragma unroll
     for (int d = 0; d < NXP; ++d) aj[d] = 0.0;
     const double* al = alpha + (long long)a * sal;
-    for (int q = 0; q < KS_CHUNK / 256; ++q) {
-        const int i = blk * KS_CHUNK + tid + 256 * q;
+    for (int q = 0; q < CH / 256; ++q) {
+        const int i = blk * CH + tid + 256 * q;
         double ks = 0.0;
         if (i < N) {
             double dist = 0.0, df[NXP];

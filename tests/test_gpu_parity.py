@@ -451,3 +451,28 @@ def test_argument_errors_fail_loudly():
     gp.replace_data_all(rng.standard_normal((5, 3)), rng.standard_normal((5, 2)))
     assert gp.get_size() == (5, 2, 1)
     gp.close()
+
+
+def test_autonomous_system_nu_zero_rollout():
+    """van_der_pol.py:20-47 pattern: no control inputs (Nu = 0), a long sequential numeric
+    gp.predict roll-out with 'ME' -- each call is one H=1 pass through the engine."""
+    import gp_mpc_b200
+    rng = np.random.default_rng(12)
+    X = rng.uniform(-2, 2, (40, 2))
+    Y = np.column_stack([X[:, 0] + 0.1 * X[:, 1], X[:, 1] + 0.1 * (-X[:, 0] + (1 - X[:, 0] ** 2) * X[:, 1])])
+    Y = Y + 2e-2 * rng.standard_normal(Y.shape)          # measurement noise, as the example adds (van_der_pol.py:66-71)
+    gp = gp_mpc_b200.GP(X, Y, normalize=True, xlb=[-2, -2], xub=[2, 2], ulb=[], uub=[], gp_method='ME',
+                        optimizer_opts={'maxiter': 100})
+    assert gp.get_size() == (40, 2, 0)
+    hy = np.column_stack([gp.get_hyper_parameters()['length_scale'], np.sqrt(gp.get_hyper_parameters()['signal_var']),
+                          np.sqrt(gp.get_hyper_parameters()['noise_var'])])
+    st = orc.data_stats(X, Y, 2)
+    model = dict(X=(X - st['meanZ']) / st['stdZ'], Y=(Y - st['meanY']) / st['stdY'], hyper=hy, normalize=True, meta=st)
+    model.update(orc.postfit(model['X'], model['Y'], hy, lapack_general_solve=False))
+    x = np.array([1.0, 0.5]); xo = x.copy()
+    for t in range(25):
+        mean, cov = gp.predict(x, [], np.zeros((2, 2)))
+        mo, co = orc.predict(model, xo, np.zeros(0), np.zeros((2, 2)), 'ME')
+        assert relinf(mean, mo) < TOL and relinf(np.diag(cov), np.diag(co)) < TOL
+        x = np.array(mean).flatten(); xo = mo.flatten()
+    gp.close()
