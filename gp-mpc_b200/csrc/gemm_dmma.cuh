@@ -237,3 +237,196 @@ static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cuda
     kern<<<grid, WM * WN * 32, BYTES, st>>>(p);
     return cudaGetLastError();
 }
+
+// =======================================================================================
+// Tile-granular TMA feed (NT products): one cp.async.bulk.tensor (SASS UTMALDG) per operand
+// per stage moves a {16 doubles x BM rows} box into a 128B-swizzled, un-padded shared tile
+// and completes on the stage's mbarrier.  Fragment loads use the k-permutation
+//     step kk, lane t  ->  k = 2 kk + (t & 1) + 8 (t >> 1)
+// (the MMA sums over k, so any permutation applied to A and B alike is valid); with the
+// 128B swizzle  chunk' = chunk ^ (row & 7)  the 16 lanes of a half-warp hit 16 distinct
+// 8-byte banks.  Same tiling / k-range / split-K / epilogue logic as gemm_dmma_kernel.
+// =======================================================================================
+#include <cuda.h>
+
+__device__ __forceinline__ void tma_tile_g2s_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+                 :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
+__global__ void __launch_bounds__(WM * WN * 32, MINB)
+gemm_dmma_tmap_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB)
+{
+    constexpr int BK = GEMM_BK;
+    constexpr int RL = BM / BN;
+    constexpr int WTM = BM / WM, WTN = BN / WN, MF = WTM / 8, NF = WTN / 8;
+    constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;            // doubles, rows of 128 B, no padding
+    constexpr uint32_t STAGE_TX = (BM + BN) * BK * 8;
+    static_assert((BM * 128) % 1024 == 0 && (BN * 128) % 1024 == 0, "tiles must be whole swizzle atoms");
+
+    extern __shared__ __align__(16) double smem_raw[];
+    double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    double* As = smem;
+    double* Bs = smem + STAGES * A_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
+
+    int it, jt;
+    long long bz = blockIdx.z;
+    int chunk = blockIdx.y;
+    if (p.lpt) {
+        it = 0; jt = p.nt - 1 - (int)blockIdx.y; bz = blockIdx.x; chunk = blockIdx.z;
+    } else if (p.lower) {
+        const int tt = blockIdx.x;
+        constexpr int R = RL > 0 ? RL : 1;
+        it = (int)((sqrt(8.0 * (double)tt / R + 1.0) - 1.0) * 0.5);
+        while (R * it * (it + 1) / 2 > tt) --it;
+        while (R * (it + 1) * (it + 2) / 2 <= tt) ++it;
+        jt = tt - R * it * (it + 1) / 2;
+    } else {
+        it = blockIdx.x / p.nt;
+        jt = blockIdx.x - it * p.nt;
+    }
+    int k_lo = 0, k_hi = p.K;
+    if (p.kflags & GEMM_KI_LE) k_hi = min(k_hi, (it + 1) * BM);
+    if (p.kflags & GEMM_KI_GE) k_lo = max(k_lo, it * BM);
+    if (p.kflags & GEMM_KJ_LE) k_hi = min(k_hi, (jt + 1) * BN);
+    if (p.kflags & GEMM_KJ_GE) k_lo = max(k_lo, jt * BN);
+    long long part_off = 0;
+    if (p.ksplit) {
+        const int cs = chunk * p.ksplit;
+        k_lo = max(k_lo, cs);
+        k_hi = min(k_hi, cs + p.ksplit);
+        if (k_lo >= k_hi) return;
+        part_off = (long long)chunk * p.sPart;
+    }
+    const int nk = (k_hi - k_lo) / BK;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto load_stage = [&](int s, int k0) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(full + s, STAGE_TX);
+            tma_tile_g2s_3d(As + s * A_STAGE, &tmA, k0, it * BM, (int)bz, full + s);
+            tma_tile_g2s_3d(Bs + s * B_STAGE, &tmB, k0, jt * BN, (int)bz, full + s);
+        }
+    };
+
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NF; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s)
+        if (s < nk) load_stage(s, k_lo + s * BK);
+
+    // swizzled fragment offsets (doubles): row r -> r*16 + ((chunk ^ (r & 7)) * 2) + (t & 1); (r & 7) == g
+    const int kperm_hi = 4 * (t >> 1), kpar = t & 1;
+    for (int kt = 0; kt < nk; ++kt) {
+        mbar_wait(full + kt % STAGES, (kt / STAGES) & 1);
+        __syncthreads();                                   // everyone is done with the stage refilled below
+        {
+            const int kn = kt + STAGES - 1;
+            if (kn < nk) load_stage(kn % STAGES, k_lo + kn * BK);
+        }
+        const int s = kt % STAGES;
+        const double* as = As + s * A_STAGE + (wm * WTM + g) * 16 + kpar;
+        const double* bs = Bs + s * B_STAGE + (wn * WTN + g) * 16 + kpar;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            const int coff = (((kk + kperm_hi) ^ g) << 1);
+            double a[MF], b[NF];
+#pragma unroll
+            for (int mi = 0; mi < MF; ++mi) a[mi] = as[mi * 8 * 16 + coff];
+#pragma unroll
+            for (int ni = 0; ni < NF; ++ni) b[ni] = bs[ni * 8 * 16 + coff];
+#pragma unroll
+            for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NF; ++ni)
+                    dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+
+    double* Cg = p.C + bz * p.sC + part_off;
+    const double* Cing = p.Cin ? (p.Cin + bz * p.sCin) : nullptr;
+    const bool diag = p.lower && ((jt + 1) * BN > it * BM);
+#pragma unroll
+    for (int mi = 0; mi < MF; ++mi) {
+        const int row = it * BM + wm * WTM + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < NF; ++ni) {
+            const int col = jt * BN + wn * WTN + ni * 8 + 2 * t;
+            double2 c;
+            c.x = p.alpha * acc[mi][ni][0];
+            c.y = p.alpha * acc[mi][ni][1];
+            if (diag && col > row) continue;
+            if (p.beta != 0.0) {
+                const double2 cin = *reinterpret_cast<const double2*>(Cing + (long long)row * p.ldcin + col);
+                c.x += p.beta * cin.x;
+                c.y += p.beta * cin.y;
+            }
+            double* dst = Cg + (long long)row * p.ldc + col;
+            if (diag && col + 1 > row) dst[0] = c.x;
+            else *reinterpret_cast<double2*>(dst) = c;
+        }
+    }
+}
+
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D map {K, rows, batch} over a row-major fp64 operand; box {16, box_rows, 1}, 128B swizzle
+static bool tmap_make(CUtensorMap* tm, const double* base, int K, int rows, int ld, long long batch_stride, int batch, int box_rows)
+{
+    static tmap_encode_fn enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+        enc = (tmap_encode_fn)fn;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)(batch > 1 ? batch_stride : (long long)rows * ld) * 8};
+    cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
+static cudaError_t gemm_tmap_launch(const GemmParams& p, int batch, int nchunks, cudaStream_t st)
+{
+    auto kern = gemm_dmma_tmap_kernel<BM, BN, WM, WN, STAGES, MINB>;
+    constexpr int BYTES = STAGES * (BM + BN) * GEMM_BK * 8 + STAGES * 8 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    CUtensorMap tmA, tmB;
+    if (!tmap_make(&tmA, p.A, p.K, p.mt * BM, p.lda, p.sA, batch, BM)) return cudaErrorInvalidValue;
+    if (!tmap_make(&tmB, p.B, p.K, p.nt * BN, p.ldb, p.sB, batch, BN)) return cudaErrorInvalidValue;
+    constexpr int R = (BM >= BN) ? BM / BN : 1;
+    const int tiles = p.lower ? R * p.mt * (p.mt + 1) / 2 : p.mt * p.nt;
+    dim3 grid(tiles, p.ksplit ? nchunks : 1, batch);
+    if (p.lpt) grid = dim3(batch, p.nt, p.ksplit ? nchunks : 1);
+    kern<<<grid, WM * WN * 32, BYTES, st>>>(p, tmA, tmB);
+    return cudaGetLastError();
+}

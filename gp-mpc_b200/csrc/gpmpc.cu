@@ -123,6 +123,11 @@ static cudaError_t gemm128(gpmpc_handle_t h, bool bt, const GemmParams& p, int b
 
 static cudaError_t gemm128_on(gpmpc_handle_t h, cudaStream_t st, bool bt, const GemmParams& p, int batch)
 {
+    if (h->opt_gemm_variant == 3 && bt) { // tile-granular TMA (tensor maps, 128B swizzle) for the NT products
+        GemmParams q = p;
+        q.nt = p.nt * 2;
+        return gemm_tmap_launch<128, 64, 2, 2, 4, 2>(q, batch, 1, st);
+    }
     if (h->opt_gemm_variant == 2) {       // variant 1 with the TMA (cp.async.bulk + mbarrier) feed
         GemmParams q = p;
         q.nt = p.nt * 2;
@@ -711,6 +716,7 @@ static int choose_ksplit(gpmpc_handle_t h)
 template <int BM>
 static cudaError_t trigemm_bm(int variant, const GemmParams& p, int batch, int nch, cudaStream_t st)
 {
+    if (variant == 3) return gemm_tmap_launch<BM, 128, 1, 8, 4, 2>(p, batch, nch, st);          // tensor-map TMA feed
     if (variant == 2) return gemm_launch<BM, 128, 1, 8, true, 3, 2, true>(p, batch, nch, st);   // TMA feed
     if (variant == 1) return gemm_launch<BM, 128, 1, 8, true, 3, 2>(p, batch, nch, st);   // 2 CTAs/SM
     return gemm_launch<BM, 128, 1, 8, true, 4, 1>(p, batch, nch, st);

@@ -10,7 +10,7 @@ from tests._util import relinf
 p = orc.synthetic_problem(1000, 8, 2, config_id=2, H=30)
 post = orc.postfit(p['X'], p['Y'], p['hyper'], lapack_general_solve=False)
 mo, vo = orc.gp_mean_var(p['X'], p['hyper'], post['alpha'], post['chol'], p['Z'])
-for gv, tv in ((2, 1), (1, 2), (2, 2)):
+for gv, tv in ((2, 1), (1, 2), (3, 1), (1, 3), (3, 3)):
     eng = gp_mpc_b200.Engine(1000, 8, 2, device=0)
     eng.set_option('gemm_variant', gv); eng.set_option('tri_variant', tv)
     eng.set_data(p['X'], p['Y']); eng.set_hyper(p['hyper']); eng.factorize()
@@ -22,14 +22,14 @@ for N in (4096, 16384):
     eng = gp_mpc_b200.Engine(N, 10, 1, device=0)
     eng.set_data(pp['X'], pp['Y']); eng.set_hyper(pp['hyper'])
     n1 = (N // 128 // 2) * 128; n2 = N - n1
-    for gv in (1, 2):
+    for gv in (1, 2, 3):
         eng.set_option('gemm_variant', gv)
         ms = eng.profile(L.PROF_SYRK, reps=5); msf = eng.profile(L.PROF_FACTORIZE, reps=2)
-        print('N=%d gemm_variant=%d (%s) syrk %.3f ms %.2f TF/s  factorize %.2f ms' % (N, gv, 'TMA' if gv == 2 else 'cp.async', ms, n2 * (n2 + 128.0) * n1 / ms / 1e9, msf), flush=True)
+        print('N=%d gemm_variant=%d (%s) syrk %.3f ms %.2f TF/s  factorize %.2f ms' % (N, gv, {1: 'cp.async', 2: 'TMA rows', 3: 'TMA tensor-map'}[gv], ms, n2 * (n2 + 128.0) * n1 / ms / 1e9, msf), flush=True)
     eng.set_option('gemm_variant', 1); eng.factorize()
-    for tv in (1, 2):
+    for tv in (1, 2, 3):
         eng.set_option('tri_variant', tv)
         for H in (50, 30):
             ms = eng.profile(L.PROF_TRIGEMM, n=H, reps=10)
-            print('N=%d tri_variant=%d (%s) H=%d %.4f ms %.2f TF/s' % (N, tv, 'TMA' if tv == 2 else 'cp.async', H, ms, H * float(N) * N / ms / 1e9), flush=True)
+            print('N=%d tri_variant=%d (%s) H=%d %.4f ms %.2f TF/s' % (N, tv, {1: 'cp.async', 2: 'TMA rows', 3: 'TMA tensor-map'}[tv], H, ms, H * float(N) * N / ms / 1e9), flush=True)
     eng.close()
