@@ -391,10 +391,20 @@ typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// 3-D map {K, rows, batch} over a row-major fp64 operand; box {16, box_rows, 1}, 128B swizzle
+// 3-D map {K, rows, batch} over a row-major fp64 operand; box {16, box_rows, 1}, 128B swizzle.
+// Encoding is a pure function of its arguments: a small cache keeps the predict path (same
+// operands every step) free of driver calls.
+struct TmapKey { const double* base; int K, rows, ld, batch, box_rows; long long bstride; };
 static bool tmap_make(CUtensorMap* tm, const double* base, int K, int rows, int ld, long long batch_stride, int batch, int box_rows)
 {
     static tmap_encode_fn enc = nullptr;
+    static TmapKey keys[64];
+    static CUtensorMap maps[64];
+    static int used = 0, next = 0;
+    const TmapKey key = {base, K, rows, ld, batch, box_rows, batch_stride};
+    for (int i = 0; i < used; ++i)
+        if (keys[i].base == key.base && keys[i].K == key.K && keys[i].rows == key.rows && keys[i].ld == key.ld &&
+            keys[i].batch == key.batch && keys[i].box_rows == key.box_rows && keys[i].bstride == key.bstride) { *tm = maps[i]; return true; }
     if (!enc) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -405,8 +415,11 @@ static bool tmap_make(CUtensorMap* tm, const double* base, int K, int rows, int 
     cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)(batch > 1 ? batch_stride : (long long)rows * ld) * 8};
     cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    const int slot = (used < 64) ? used++ : (next++ & 63);
+    keys[slot] = key; maps[slot] = *tm;
+    return true;
 }
 
 template <int BM, int BN, int WM, int WN, int STAGES, int MINB>

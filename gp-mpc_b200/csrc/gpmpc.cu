@@ -88,7 +88,7 @@ struct gpmpc_handle_s {
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 1, opt_tri_variant = 1, opt_leaf_variant = 1;
+    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 3, opt_tri_variant = 3, opt_leaf_variant = 1;
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     // peer (CUDA IPC) exchange: [flags: 2*MAXW u64][gather buffer parity 0][parity 1]
@@ -123,10 +123,15 @@ static cudaError_t gemm128(gpmpc_handle_t h, bool bt, const GemmParams& p, int b
 
 static cudaError_t gemm128_on(gpmpc_handle_t h, cudaStream_t st, bool bt, const GemmParams& p, int batch)
 {
-    if (h->opt_gemm_variant == 3 && bt) { // tile-granular TMA (tensor maps, 128B swizzle) for the NT products
+    if (h->opt_gemm_variant == 3) {
+        // tile-granular TMA (tensor maps, 128B swizzle) for the NT products that fill the GPU for at
+        // least two waves; everything else (NN products, small launches) takes the cp.async variant
+        const long long tiles = (long long)batch * (p.lower ? (long long)p.mt * (p.mt + 1) : 2LL * p.mt * p.nt);
         GemmParams q = p;
         q.nt = p.nt * 2;
-        return gemm_tmap_launch<128, 64, 2, 2, 4, 2>(q, batch, 1, st);
+        if (bt && tiles >= 592) return gemm_tmap_launch<128, 64, 2, 2, 4, 2>(q, batch, 1, st);
+        return bt ? gemm_launch<128, 64, 2, 2, true, 3, 2>(q, batch, 1, st)
+                  : gemm_launch<128, 64, 2, 2, false, 3, 2>(q, batch, 1, st);
     }
     if (h->opt_gemm_variant == 2) {       // variant 1 with the TMA (cp.async.bulk + mbarrier) feed
         GemmParams q = p;
