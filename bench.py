@@ -307,7 +307,7 @@ def main():
             traffic = n * tj['trigemm_N16384_H50_per_output_bytes']
     except Exception:
         pass
-    roofline = {'bound': 'tensor', 'kernel': 'gemm_dmma_kernel<BM,128,1,8,NT> (v = Linv ks, split-K)',
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_dmma_tmap_kernel<BM,128,1,8,4,2> (v = Linv ks: DMMA fed by TMA tensor maps, split-K, longest-first)',
                 'achieved': achieved, 'peak': dgemm_tf, 'unit': 'TFLOP/s', 'frac': achieved / dgemm_tf,
                 'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (fp64 is absent from MEASURED_PEAKS.json)',
                 'ms_per_launch': ms_tri, 'traffic': traffic, 'algorithmic_bytes': n * 4.0 * N * N,
