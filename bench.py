@@ -212,10 +212,27 @@ def main():
         box = [eng.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         eng.comm_init(box[0], rank, world)
+        peer_mode = False
         if os.environ.get('GPMPC_NO_PEER', '0') != '1':     # fused epilogue + all-gather over peer memory
+            try:
+                mine = eng.peer_export(max(64, H))
+            except Exception:
+                mine = None
             hs = [None] * world
-            dist.all_gather_object(hs, eng.peer_export(max(64, H)))
-            eng.peer_attach(hs)
+            dist.all_gather_object(hs, mine)
+            ok = all(x is not None for x in hs)
+            if ok:
+                try:
+                    eng.peer_attach(hs)
+                except Exception:
+                    ok = False
+            oks = [None] * world
+            dist.all_gather_object(oks, ok)
+            peer_mode = all(oks)
+            if not peer_mode:                                # collective fallback to the NCCL gather
+                eng.set_option('peer', 0)
+    else:
+        peer_mode = False
     eng.factorize()
     t_setup = time.perf_counter() - t0
 
@@ -340,8 +357,7 @@ def main():
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': wl['name'], 'method': 'TA', 'N': N, 'Nx': Nx, 'Ny': Ny, 'H': H,
                            'parallelism': 'outputs sharded %d/GPU, %s' % (n, 'single GPU' if world == 1 else (
-                               'NCCL all-gather' if os.environ.get('GPMPC_NO_PEER', '0') == '1' else
-                               'epilogue stores to NVLink peer buffers (fused all-gather), NCCL fallback')),
+                               'epilogue stores to NVLink peer buffers (fused all-gather)' if peer_mode else 'NCCL all-gather')),
                            'l2': 'flush 256MB between steps' if flush else 'model %.1f GB/rank > L2, no flush' % (model_bytes / 1e9),
                            'setup_s': t_setup},
                 'clocks': clocks,

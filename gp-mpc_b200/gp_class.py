@@ -124,8 +124,26 @@ class GP:
             self.__engine.comm_init(uid, c.rank, c.world)
             # fused epilogue + all-gather over NVLink peer memory (CUDA IPC); NCCL stays the fallback
             if hasattr(self.__engine, 'peer_export') and os.environ.get('GPMPC_NO_PEER', '0') != '1':
-                handles = c.allgather_object(self.__engine.peer_export(int(os.environ.get('GPMPC_PEER_HCAP', 256))))
-                self.__engine.peer_attach(handles)
+                self.__attach_peers(c)
+
+    def __attach_peers(self, c):
+        """CUDA-IPC exchange blocks for the fused epilogue/all-gather.  The decision is collective:
+        if any rank cannot export or map a peer block (no P2P, IPC disabled in the container),
+        every rank falls back to the NCCL gather."""
+        eng = self.__engine
+        try:
+            mine = eng.peer_export(int(os.environ.get('GPMPC_PEER_HCAP', 256)))
+        except Exception:
+            mine = None
+        handles = c.allgather_object(mine)
+        ok = all(hd is not None for hd in handles)
+        if ok:
+            try:
+                eng.peer_attach(handles)
+            except Exception:
+                ok = False
+        if not all(c.allgather_object(ok)):
+            eng.set_option('peer', 0)
 
     def __factorize(self):
         self.__engine.set_hyper(self.__hyper)
