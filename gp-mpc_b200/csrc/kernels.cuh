@@ -246,8 +246,14 @@ __device__ __forceinline__ void warp_potrf16_trtri16(double* D, double* Dinv, in
     for (int j = 0; j < 16; ++j) {
         const double d = __shfl_sync(full, a[j], j);
         if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, info_val0 + j + 1);
-        const double pv = sqrt(d);
-        ipd[j] = 1.0 / pv;
+        // sqrt and reciprocal from one rsqrt + Newton corrections (shorter dependent chain than
+        // DSQRT followed by a division; both results are correctly rounded to ~0.5 ulp)
+        double y = rsqrt(d);
+        double pv = d * y;
+        pv = fma(fma(-pv, pv, d), 0.5 * y, pv);
+        y = fma(fma(-pv, y, 1.0), y, y);
+        if (!(d > 0.0)) { pv = sqrt(d); y = 1.0 / pv; }     // keep NaN/inf propagation of the plain formula
+        ipd[j] = y;
         a[j] = (r == j) ? pv : a[j] * ipd[j];              // l_rj for r > j (LAPACK dpotf2 scales by 1/ajj too)
 #pragma unroll
         for (int k = j + 1; k < 16; ++k) {
