@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #define GPMPC_TILE 128          // all internal matrices are padded to a multiple of this
+#define GPMPC_MAX_DEVICES 64
 
 #define CUDA_TRY(expr)                                                        \
     do {                                                                      \

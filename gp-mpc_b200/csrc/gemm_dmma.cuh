@@ -224,11 +224,13 @@ static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cuda
     using SM = GemmSmem<BM, BN, BT, STAGES>;
     auto kern = gemm_dmma_kernel<BM, BN, WM, WN, BT, STAGES, MINB, TMA>;
     constexpr int BYTES = SM::BYTES + (TMA ? STAGES * 8 : 0);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[GPMPC_MAX_DEVICES] = {false};       // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < GPMPC_MAX_DEVICES && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     constexpr int R = (BM >= BN) ? BM / BN : 1;
     const int tiles = p.lower ? R * p.mt * (p.mt + 1) / 2 : p.mt * p.nt;
@@ -248,6 +250,7 @@ static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cuda
 // 8-byte banks.  Same tiling / k-range / split-K / epilogue logic as gemm_dmma_kernel.
 // =======================================================================================
 #include <cuda.h>
+#include <mutex>
 
 __device__ __forceinline__ void tma_tile_g2s_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar)
 {
@@ -401,6 +404,8 @@ static bool tmap_make(CUtensorMap* tm, const double* base, int K, int rows, int 
     static TmapKey keys[64];
     static CUtensorMap maps[64];
     static int used = 0, next = 0;
+    static std::mutex mtx;                                       // handles on different threads share the cache
+    std::lock_guard<std::mutex> lock(mtx);
     const TmapKey key = {base, K, rows, ld, batch, box_rows, batch_stride};
     for (int i = 0; i < used; ++i)
         if (keys[i].base == key.base && keys[i].K == key.K && keys[i].rows == key.rows && keys[i].ld == key.ld &&
@@ -427,11 +432,13 @@ static cudaError_t gemm_tmap_launch(const GemmParams& p, int batch, int nchunks,
 {
     auto kern = gemm_dmma_tmap_kernel<BM, BN, WM, WN, STAGES, MINB>;
     constexpr int BYTES = STAGES * (BM + BN) * GEMM_BK * 8 + STAGES * 8 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[GPMPC_MAX_DEVICES] = {false};       // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < GPMPC_MAX_DEVICES && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     CUtensorMap tmA, tmB;
     if (!tmap_make(&tmA, p.A, p.K, p.mt * BM, p.lda, p.sA, batch, BM)) return cudaErrorInvalidValue;

@@ -162,11 +162,11 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
 {
     const int ld = h->Npad;
     if (n <= LEAF_N) {
-        static bool conf = false;
-        if (!conf) {
+        static bool conf[GPMPC_MAX_DEVICES] = {false};
+        if (!conf[h->device % GPMPC_MAX_DEVICES]) {
             CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_N * LEAF_LD * 8));
             CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_DOUBLES * 8));
-            conf = true;
+            conf[h->device % GPMPC_MAX_DEVICES] = true;
         }
         if (h->opt_leaf_variant == 0)
             leaf_potrf_trtri_kernel<<<batch, 256, LEAF_N * LEAF_LD * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
@@ -247,13 +247,13 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
 // output slabs at K (stride slab).  full = 1 writes the whole square, 0 the lower triangle.
 static int launch_kbuild(gpmpc_handle_t h, const double* dHyp, const double* dJit, double* K, int batch, int full)
 {
-    static bool conf = false;
+    static bool conf[GPMPC_MAX_DEVICES] = {false};
     const int KD = (h->Nx + 3) & ~3, S = ((KD >> 2) & 1) ? KD : KD + 4;
     const int smem = (2 * KB2_TILE * S + 2 * KB2_TILE + 16) * 8;
-    if (!conf) {
+    if (!conf[h->device % GPMPC_MAX_DEVICES]) {
         CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * KB2_TILE * 36 + 2 * KB2_TILE + 16) * 8));
-        conf = true;
+        conf[h->device % GPMPC_MAX_DEVICES] = true;
     }
     const int T = h->Npad / KB2_TILE;
     dim3 grid(T * (T + 1) / 2, 1, batch);
