@@ -34,6 +34,7 @@ SYMBOLS = [
     ('gpmpc_factorize', C.c_int, [_H, C.c_double, _ip]),
     ('gpmpc_nlml', C.c_int, [_H, C.c_int, _dp, _dp, _dp]),
     ('gpmpc_predict', C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]),
+    ('gpmpc_append', C.c_int, [_H, _dp, _dp]),
     ('gpmpc_posterior_cov', C.c_int, [_H, C.c_int, _dp, _dp]),
     ('gpmpc_predict_device', C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -186,6 +187,17 @@ class Engine:
         self._check(self.lib.gpmpc_predict(self.h, int(method), H, _ptr(Z), _ptr(Sigma), spp,
                                            _ptr(mean), _ptr(var), _ptr(cov), _ptr(jac)))
         return mean, var, cov, jac
+
+    def append(self, x_new, y_new):
+        """Rank-1 append of one training point; returns False when the padded capacity is full
+        or positive definiteness is lost (caller refits), True on success."""
+        x = _f64(x_new, (self.Nx,)); y = _f64(y_new, (self.Ny,))
+        rc = self.lib.gpmpc_append(self.h, _ptr(x), _ptr(y))
+        if rc in (ERR_STATE, ERR_NOTPD):
+            return False
+        self._check(rc)
+        self.N += 1
+        return True
 
     def posterior_cov(self, Z):
         """(out_count, H, H): sf2 - V^T V per owned output (GP.covar)."""

@@ -1089,6 +1089,56 @@ extern "C" int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* 
     return GPMPC_OK;
 }
 
+extern "C" int gpmpc_append(gpmpc_handle_t h, const double* x_new, const double* y_new)
+{
+    if (!h || !x_new || !y_new) return GPMPC_ERR_ARG;
+    if (!h->factorized) { set_error(h, "gpmpc_append: call gpmpc_factorize first"); return GPMPC_ERR_STATE; }
+    if (h->N >= h->Npad) { set_error(h, "gpmpc_append: capacity %d reached, refit on a new handle", h->Npad); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_predict_bufs(h, 1);
+    if (rc) return rc;
+    const int N = h->N, Nx = h->Nx, np = h->Npad, nl = h->nloc;
+    // k(X, x_new) for every owned output through the predict ks kernel (H = 1): row 0 of KS^T
+    CUDA_TRY(cudaMemcpyAsync(h->dZ, x_new, Nx * 8, cudaMemcpyHostToDevice, h->st));
+    CUDA_TRY(launch_ks_any(h, h->dZ, 1, 8, (np + ks_chunk(h) - 1) / ks_chunk(h)));
+    // l = Li k (rows < N), r = Li^T l
+    if (!h->dV) { ALLOC(h->dV, (long long)nl * HB * np); ALLOC(h->dR, (long long)nl * HB * np); }
+    dim3 g1((np + 7) / 8, 1, nl);
+    trmv_lower_kernel<<<g1, 256, 0, h->st>>>(h->dLi, np, slab(h), h->dKST, (long long)HB * np, h->dV, (long long)HB * np, N);
+    CUDA_TRY(cudaGetLastError());
+    // rows >= N of l must be zero for the transposed product over the padded matrix
+    for (int a = 0; a < nl; ++a)
+        CUDA_TRY(cudaMemsetAsync(h->dV + (long long)a * HB * np + N, 0, (size_t)(np - N) * 8, h->st));
+    dim3 g2(np / 32, 1, nl);
+    trmv_lower_T_kernel<<<g2, 256, 0, h->st>>>(h->dLi, np, slab(h), h->dV, (long long)HB * np, h->dR, (long long)HB * np, np);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(h->dInfo, 0, nl * sizeof(int), h->st));
+    append_row_kernel<<<nl, 256, 0, h->st>>>(h->dL, h->dLi, np, slab(h), h->dV, h->dR, (long long)HB * np, h->dHyp, Nx + 2, Nx, N, h->dInfo);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<int> inf(nl, 0);
+    CUDA_TRY(cudaMemcpyAsync(inf.data(), h->dInfo, nl * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    // the new point joins X^T (column N) and Y
+    for (int d = 0; d < Nx; ++d) CUDA_TRY(cudaMemcpyAsync(h->dXT + (long long)d * np + N, x_new + d, 8, cudaMemcpyHostToDevice, h->st));
+    for (int a = 0; a < nl; ++a) CUDA_TRY(cudaMemcpyAsync(h->dY + (long long)a * np + N, y_new + h->a0 + a, 8, cudaMemcpyHostToDevice, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    for (int a = 0; a < nl; ++a)
+        if (inf[a]) {
+            h->factorized = false;       // row N of that output is unusable: the caller must refactorise
+            set_error(h, "gpmpc_append: output %d lost positive definiteness (refactorise, jitter applies there)", h->a0 + a);
+            h->N = N + 1;
+            return GPMPC_ERR_NOTPD;
+        }
+    h->N = N + 1;
+    h->em_kinv_valid = false;
+    rc = launch_alpha(h, 0, nl);
+    if (rc) return rc;
+    std::vector<double> res(2 * nl);
+    CUDA_TRY(cudaMemcpyAsync(res.data(), h->dRes, 2 * nl * 8, cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    for (int a = 0; a < nl; ++a) { h->logdet[a] = res[2 * a]; h->yalpha[a] = res[2 * a + 1]; }
+    return GPMPC_OK;
+}
+
 extern "C" int gpmpc_posterior_cov(gpmpc_handle_t h, int H, const double* Z, double* out)
 {
     if (!h || !Z || !out || H < 1) return GPMPC_ERR_ARG;

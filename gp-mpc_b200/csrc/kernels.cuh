@@ -1046,3 +1046,42 @@ __global__ void em_finalize_kernel(int Nx, int Ny, int npairs, const double* __r
         if (a == b && var) var[a] = c;
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// Rank-1 append of one training point (the reference's update_data,
+// gp_class.py:384-471, is self-declared broken -- this is the textbook update):
+//   l = L^-1 k(X, x_new);  lambda = sqrt(k(x_new,x_new) + sn2 - l^T l)
+//   L    <- [[L, 0], [l^T, lambda]]          L^-1 <- [[L^-1, 0], [-(l^T L^-1)/lambda, 1/lambda]]
+// lvec = L^-1 k, rvec = (L^-1)^T lvec are produced by the trmv kernels; this kernel writes
+// row N of both factors (the identity tail row it replaces).  One CTA per output.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+append_row_kernel(double* __restrict__ L, double* __restrict__ Li, int ld, long long sL,
+                  const double* __restrict__ lvec, const double* __restrict__ rvec, long long sv,
+                  const double* __restrict__ hyp, int hyp_ld, int Nx, int N, int* __restrict__ info)
+{
+    __shared__ double red[8];
+    __shared__ double lam_s;
+    const int a = blockIdx.x, tid = threadIdx.x;
+    const double* lv = lvec + (long long)a * sv;
+    const double* rv = rvec + (long long)a * sv;
+    double s = 0.0;
+    for (int i = tid; i < N; i += 256) s = fma(lv[i], lv[i], s);
+    s = warp_sum(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double r = 0.0;
+        for (int w = 0; w < 8; ++w) r += red[w];
+        const double sf = hyp[(long long)a * hyp_ld + Nx], sn = hyp[(long long)a * hyp_ld + Nx + 1];
+        const double d = sf * sf + sn * sn - r;
+        if (!(d > 0.0)) atomicCAS(info + a, 0, N + 1);
+        lam_s = sqrt(d);
+    }
+    __syncthreads();
+    const double lam = lam_s, il = 1.0 / lam;
+    double* Lr = L + (long long)a * sL + (long long)N * ld;
+    double* Lir = Li + (long long)a * sL + (long long)N * ld;
+    for (int j = tid; j < N; j += 256) { Lr[j] = lv[j]; Lir[j] = -rv[j] * il; }
+    if (tid == 0) { Lr[N] = lam; Lir[N] = il; }
+}

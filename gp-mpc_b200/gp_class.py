@@ -430,6 +430,30 @@ class GP:
         self.__factorize()
         self.set_method(self.__gp_method)
 
+    def append_data(self, X_new, Y_new):
+        """ Add observations one at a time with the O(N^2) rank-1 update of L, L^-1 and alpha
+        (what the reference's ``update_data``, gp_class.py:384-471, set out to do); hyper-
+        parameters are kept.  Falls back to a full refactorisation (``update_data_all``) when the
+        padded capacity is exhausted or an update loses positive definiteness. """
+        X_new = np.array(X_new, dtype=np.float64).reshape(-1, self.__Nx)
+        Y_new = np.array(Y_new, dtype=np.float64).reshape(-1, self.__Ny)
+        Xs, Ys = X_new, Y_new
+        if self.__normalize:
+            Ys = self.standardize(Y_new, self.__meanY, self.__stdY)
+            Xs = self.standardize(X_new, self.__meanZ, self.__stdZ)
+        for k in range(Xs.shape[0]):
+            if not self.__engine.append(Xs[k], Ys[k]):
+                self.__X = np.vstack([self.__X, Xs[k:]])
+                self.__Y = np.vstack([self.__Y, Ys[k:]])
+                self.__N = self.__X.shape[0]
+                self.__build_engine()
+                self.__factorize()
+                return
+            self.__X = np.vstack([self.__X, Xs[k:k + 1]])
+            self.__Y = np.vstack([self.__Y, Ys[k:k + 1]])
+            self.__N = self.__X.shape[0]
+        self.__invK = None
+
     def replace_data_all(self, X_new, Y_new):
         """ Replace training data with new observations  (reference gp_class.py:553-626) """
         X_new = np.array(X_new, dtype=np.float64).copy()

@@ -108,6 +108,13 @@ int gpmpc_nlml(gpmpc_handle_t h, int a, const double* theta, double* nll, double
 int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* Z, const double* Sigma,
                   int sigma_per_point, double* mean, double* var, double* cov, double* jac);
 
+/* Append ONE training point (x_new:(Nx,), y_new:(Ny,) host, GP input space) to a factorised
+ * model in O(N^2): new rows of L and L^-1, alpha refreshed.  Capacity is the padded size
+ * ceil(N/128)*128 (GPMPC_ERR_STATE beyond it: refit on a new handle).  GPMPC_ERR_NOTPD if the
+ * Schur complement is not positive: refactorise (the jitter policy applies there).  The correct
+ * counterpart of the reference's broken GP.update_data (gp_class.py:384-471). */
+int gpmpc_append(gpmpc_handle_t h, const double* x_new, const double* y_new);
+
 /* Full posterior covariance between H test points for every OWNED output:
  * out:(out_count,H,H) host, out[a] = sf2_a - V_a^T V_a with V_a = L_a \ k(X, Z)  (the scalar
  * kss = sf2 is broadcast over the whole matrix exactly as the reference does).  Replaces

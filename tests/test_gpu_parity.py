@@ -476,3 +476,30 @@ def test_autonomous_system_nu_zero_rollout():
         assert relinf(mean, mo) < TOL and relinf(np.diag(cov), np.diag(co)) < TOL
         x = np.array(mean).flatten(); xo = mo.flatten()
     gp.close()
+
+
+def test_rank1_append_matches_a_full_refit():
+    """O(N^2) append of training points == refactorising from scratch (oracle
+    postfit on the concatenated data); crossing the padded capacity falls back to a refit."""
+    import gp_mpc_b200
+    p = orc.synthetic_problem(134, 5, 2, config_id=31, H=12)
+    X, Y, hyper = p['X'], p['Y'], p['hyper']
+    gp = gp_mpc_b200.GP(X[:123], Y[:123], normalize=False, hyper=dict(hyper=hyper))
+    gp.append_data(X[123:128], Y[123:128])                  # fills the 128-row capacity by rank-1 updates
+    assert gp.get_size()[0] == 128 and gp.engine.N == 128
+    post = orc.postfit(X[:128], Y[:128], hyper, lapack_general_solve=False)
+    assert relinf(gp.get_chol(), post['chol']) < 1e-10
+    assert relinf(gp.get_alpha(), post['alpha']) < 1e-7
+    mo, vo = orc.gp_mean_var(X[:128], hyper, post['alpha'], post['chol'], p['Z'])
+    mean, var, _, _ = gp.engine.predict(p['Z'], None, _L().METHOD_ME, want_jac=False)
+    assert relinf(mean, mo) < TOL and relinf(var, vo) < TOL
+    gp.append_data(X[128:], Y[128:])                        # capacity exceeded -> refit path
+    assert gp.get_size()[0] == 134
+    post = orc.postfit(X, Y, hyper, lapack_general_solve=False)
+    assert relinf(gp.get_chol(), post['chol']) < 1e-10
+    gp.append_data(X[:1] + 0.37, Y[:1])                     # rank-1 again on the new 256-row handle
+    assert gp.get_size()[0] == 135
+    Xa = np.vstack([X, X[:1] + 0.37]); Ya = np.vstack([Y, Y[:1]])
+    post = orc.postfit(Xa, Ya, hyper, lapack_general_solve=False)
+    assert relinf(gp.get_chol(), post['chol']) < 1e-10 and relinf(gp.get_alpha(), post['alpha']) < 1e-7
+    gp.close()
