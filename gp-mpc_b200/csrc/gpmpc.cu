@@ -88,7 +88,7 @@ struct gpmpc_handle_s {
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 3, opt_tri_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 1;
+    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 3, opt_tri_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 148;   // 128x64-tile count below which 64x32 tiles are used
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     // peer (CUDA IPC) exchange: [flags: 2*MAXW u64][gather buffer parity 0][parity 1]
@@ -128,7 +128,7 @@ static cudaError_t gemm128_on(gpmpc_handle_t h, cudaStream_t st, bool bt, const 
         // least two waves; everything else (NN products, small launches) takes the cp.async variant
         const long long tiles = (long long)batch * (p.lower ? (long long)p.mt * (p.mt + 1) : 2LL * p.mt * p.nt);
         GemmParams q = p;
-        if (tiles < 148 && h->opt_small_tiles) {
+        if (tiles < h->opt_small_tiles) {
             // deep recursion levels: a handful of 128x64 tiles cannot occupy 148 SMs; 64x32 tiles
             // (8x more CTAs, 4 CTAs/SM) cut the latency of these critical-path launches
             q.mt = p.mt * 2; q.nt = p.nt * 4;
@@ -672,7 +672,7 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
     }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "tri_variant")) { h->opt_tri_variant = (int)value; return GPMPC_OK; }
-    if (!strcmp(name, "small_tiles")) { h->opt_small_tiles = value != 0.0; return GPMPC_OK; }
+    if (!strcmp(name, "small_tiles")) { h->opt_small_tiles = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "peer")) { h->opt_peer = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "leaf_variant")) { h->opt_leaf_variant = (int)value; return GPMPC_OK; }

@@ -6,9 +6,9 @@ import gp_mpc_b200
 from gp_mpc_b200 import _lib as L
 from oracle import gp_oracle as orc
 from tests._util import relinf
-for N in (500, 1000, 2048, 4096, 8192, 16384):
+for N in (1000, 4096, 8192, 16384):
     p = orc.synthetic_problem(N, 10, 1, config_id=5, H=50)
-    for stv in (0, 1):
+    for stv in (148, 296, 444, 592):
         eng = gp_mpc_b200.Engine(N, 10, 1, device=0)
         eng.set_option('small_tiles', stv)
         eng.set_data(p['X'], p['Y']); eng.set_hyper(p['hyper'])
