@@ -88,7 +88,7 @@ struct gpmpc_handle_s {
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 3, opt_tri_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 148;   // 128x64-tile count below which 64x32 tiles are used
+    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 3, opt_tri_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 592;   // 128x64-tile count below which 64x32 tiles are used
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     // peer (CUDA IPC) exchange: [flags: 2*MAXW u64][gather buffer parity 0][parity 1]
