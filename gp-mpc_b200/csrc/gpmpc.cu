@@ -17,7 +17,7 @@
 
 #define GPMPC_VERSION 100
 #define HB 64                 // test points per predict pass (rows of the KS^T operand)
-#define MAX_CHUNKS 16         // split-K partial slots per output
+#define MAX_CHUNKS 32         // split-K partial slots per output
 #define NX_MAX 32
 #define MAX_DEPTH 12           // recursion depth bound: 128 * 2^12 rows
 
