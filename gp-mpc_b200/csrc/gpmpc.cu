@@ -715,15 +715,44 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
     return GPMPC_OK;
 }
 
+// Split-K chunk of the predict product.  Work item (j-tile, chunk) costs its k-tiles plus a fixed
+// prologue/epilogue; items are dispatched longest-first onto 2 CTA slots per SM.  The chunk is
+// picked by simulating that list schedule for a few candidates (cheap: <= a few thousand items)
+// -- more chunks balance the triangular workload, fewer chunks save per-item overhead and
+// partial-sum traffic.
 static int choose_ksplit(gpmpc_handle_t h)
 {
     const int np = h->Npad, nt = np / 128;
     if (h->opt_ksplit) return h->opt_ksplit >= np ? 0 : std::max(h->opt_ksplit, (np / MAX_CHUNKS + 127) / 128 * 128);
-    // longest-first dispatch bounds the makespan by total/148 + longest item: keep the longest
-    // item (one chunk of k-tiles) at ~10 % of an SM's share, at least 2 k-tiles, at most 16 chunks
-    long long ks = std::max<long long>(2, (long long)h->nloc * nt * nt / 2960) * 128;
-    ks = std::max<long long>(ks, (np / MAX_CHUNKS + 127) / 128 * 128);
-    return ks >= np ? 0 : (int)ks;
+    static int cache_np = -1, cache_nl = -1, cache_ks = 0;
+    if (cache_np == np && cache_nl == h->nloc) return cache_ks;
+    const int cands[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 1 << 20};
+    const int slots = 296;
+    const double overhead = 0.5;           // k-tile equivalents per item (pipeline fill, partial store, reduce)
+    const int cap = std::max(2, nt / 8);   // measured: chunks longer than N/8 lose to the tail (two CTAs share an SM)
+    double best = 1e300; int best_tiles = 1 << 20;
+    std::vector<double> slot(slots);
+    for (int ct : cands) {
+        if (ct < nt && ct > cap && nt > 16) continue;
+        const int nch = (ct >= nt) ? 1 : (nt + ct - 1) / ct;
+        if (nch > MAX_CHUNKS) continue;
+        std::fill(slot.begin(), slot.end(), 0.0);
+        // dispatch order of the kernel: chunk-major, j-tile descending, outputs innermost
+        for (int c = 0; c < nch; ++c)
+            for (int jt = nt - 1; jt >= 0; --jt) {
+                const int lo = (ct >= nt) ? 0 : c * ct, hi = std::min(jt + 1, (ct >= nt) ? nt : (c + 1) * ct);
+                if (hi <= lo) continue;
+                for (int a = 0; a < h->nloc; ++a) {
+                    auto it = std::min_element(slot.begin(), slot.end());
+                    *it += (hi - lo) + overhead;
+                }
+            }
+        const double mk = *std::max_element(slot.begin(), slot.end());
+        if (mk < best - 1e-9) { best = mk; best_tiles = ct; }
+    }
+    cache_np = np; cache_nl = h->nloc;
+    cache_ks = (best_tiles >= nt) ? 0 : best_tiles * 128;
+    return cache_ks;
 }
 
 template <int BM>
