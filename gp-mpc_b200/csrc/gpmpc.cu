@@ -76,6 +76,7 @@ struct gpmpc_handle_s {
     // predict
     double *dKST = nullptr, *dPart = nullptr, *dPMJ = nullptr, *dSQ = nullptr, *dV = nullptr, *dR = nullptr;
     double *dG = nullptr, *dZ = nullptr, *dSigma = nullptr, *dMean = nullptr, *dVar = nullptr, *dJ = nullptr, *dCov = nullptr;
+    double *dIn = nullptr, *dOut = nullptr;   // [Z | Sigma] and [mean | var | J | cov] slabs: one H2D + one D2H per host call
     int Hcap = 0;
     double* hPinned = nullptr; size_t hPinnedBytes = 0;
     // nlml scratch
@@ -94,7 +95,7 @@ struct gpmpc_handle_s {
     // peer (CUDA IPC) exchange: [flags: 2*MAXW u64][gather buffer parity 0][parity 1]
     double* dPeerBlock = nullptr; long long peerGsz = 0; int peerHcap = 0; bool peer_ready = false;
     double* peerBase[GPMPC_MAXW] = {nullptr}; bool peerOpened[GPMPC_MAXW] = {false};
-    unsigned int* dPeerCounter = nullptr; int* dPeerStatus = nullptr;
+    unsigned int* dPeerCounter = nullptr; int* dPeerStatus = nullptr; int* hPeerStatus = nullptr;
     unsigned long long peer_step = 0; int opt_peer = 1;
     char err[512] = "";
 };
@@ -416,10 +417,9 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     for (int r = 0; r < GPMPC_MAXW; ++r) if (h->peerOpened[r]) cudaIpcCloseMemHandle(h->peerBase[r]);
     if (h->dPeerBlock) cudaFree(h->dPeerBlock);
     if (h->dPeerCounter) cudaFree(h->dPeerCounter);
-    if (h->dPeerStatus) cudaFree(h->dPeerStatus);
+    if (h->hPeerStatus) cudaFreeHost(h->hPeerStatus);
     double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
-                      h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dG, h->dZ, h->dSigma, h->dMean,
-                      h->dVar, h->dJ, h->dCov, h->dU, h->dKinv, h->dGradPart, h->dGrad,
+                      h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dG, h->dIn, h->dOut, h->dU, h->dKinv, h->dGradPart, h->dGrad,
                       h->dKinvAll, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
@@ -698,19 +698,19 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
     }
     if (H > h->Hcap) {
         CUDA_TRY(cudaStreamSynchronize(h->st));
-        double* bufs[] = {h->dG, h->dZ, h->dSigma, h->dMean, h->dVar, h->dJ, h->dCov};
+        double* bufs[] = {h->dG, h->dIn, h->dOut};
         for (double* b : bufs) if (b) cudaFree(b);
-        h->dG = h->dZ = h->dSigma = h->dMean = h->dVar = h->dJ = h->dCov = nullptr;
-        const int cap = std::max(H, HB);
+        h->dG = h->dIn = h->dOut = nullptr;
+        const long long cap = std::max(H, HB);
         const int nyp = h->nloc_max * h->world;
-        ALLOC(h->dG, (long long)nyp * cap * (h->Nx + 2));
-        ALLOC(h->dZ, (long long)cap * h->Nx);
-        ALLOC(h->dSigma, (long long)cap * h->Nx * h->Nx);
-        ALLOC(h->dMean, (long long)cap * h->Ny);
-        ALLOC(h->dVar, (long long)cap * h->Ny);
-        ALLOC(h->dJ, (long long)cap * h->Ny * h->Nx);
-        ALLOC(h->dCov, (long long)cap * h->Ny * h->Ny);
-        h->Hcap = cap;
+        const long long Nx = h->Nx, Ny = h->Ny;
+        ALLOC(h->dG, (long long)nyp * cap * (Nx + 2));
+        ALLOC(h->dIn, cap * Nx + cap * Nx * Nx);
+        ALLOC(h->dOut, cap * (2 * Ny + Ny * Nx + Ny * Ny));
+        h->dZ = h->dIn; h->dSigma = h->dIn + cap * Nx;
+        h->dMean = h->dOut; h->dVar = h->dOut + cap * Ny; h->dJ = h->dOut + 2 * cap * Ny;
+        h->dCov = h->dOut + 2 * cap * Ny + cap * Ny * Nx;
+        h->Hcap = (int)cap;
     }
     return GPMPC_OK;
 }
@@ -1051,11 +1051,10 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
 static int peer_status_check(gpmpc_handle_t h)
 {
     if (!h->peer_ready) return GPMPC_OK;
-    int st = 0;
-    CUDA_TRY(cudaMemcpy(&st, h->dPeerStatus, sizeof(int), cudaMemcpyDeviceToHost));
+    const int st = h->hPeerStatus ? *(volatile int*)h->hPeerStatus : 0;
     if (st) {
         set_error(h, "peer exchange timed out waiting for rank %d (step %llu)", st - 1, h->peer_step);
-        cudaMemset(h->dPeerStatus, 0, sizeof(int));
+        *h->hPeerStatus = 0;
         return GPMPC_ERR_NCCL;
     }
     return GPMPC_OK;
@@ -1102,27 +1101,33 @@ extern "C" int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* 
     const int Nx = h->Nx, Ny = h->Ny;
     const size_t nz = (size_t)H * Nx, ns = (method == GPMPC_METHOD_TA && Sigma) ? (size_t)(spp ? H : 1) * Nx * Nx : 0;
     const size_t nm = (size_t)H * Ny, nj = (size_t)H * Ny * Nx, nc = (size_t)H * Ny * Ny;
-    rc = ensure_pinned(h, (nz + ns + 2 * nm + nj + nc) * 8);
+    // device slabs: [Z | Sigma] and [mean | var | J | cov] at capacity-based offsets -> one copy each way
+    const size_t cap = (size_t)h->Hcap;
+    const size_t in_span = ns ? cap * Nx + ns : nz;
+    const size_t off_var = cap * Ny, off_j = 2 * cap * Ny, off_c = 2 * cap * Ny + cap * Ny * Nx;
+    size_t lo = (size_t)-1, hi = 0;
+    if (mean) { lo = std::min(lo, (size_t)0); hi = std::max(hi, nm); }
+    if (var) { lo = std::min(lo, off_var); hi = std::max(hi, off_var + nm); }
+    if (jac) { lo = std::min(lo, off_j); hi = std::max(hi, off_j + nj); }
+    if (cov) { lo = std::min(lo, off_c); hi = std::max(hi, off_c + nc); }
+    const size_t out_span = (hi > lo) ? hi - lo : 0;
+    rc = ensure_pinned(h, (in_span + out_span) * 8);
     if (rc) return rc;
     double* pin = h->hPinned;
     memcpy(pin, Z, nz * 8);
-    if (ns) memcpy(pin + nz, Sigma, ns * 8);
-    CUDA_TRY(cudaMemcpyAsync(h->dZ, pin, nz * 8, cudaMemcpyHostToDevice, h->st));
-    if (ns) CUDA_TRY(cudaMemcpyAsync(h->dSigma, pin + nz, ns * 8, cudaMemcpyHostToDevice, h->st));
+    if (ns) memcpy(pin + cap * Nx, Sigma, ns * 8);
+    CUDA_TRY(cudaMemcpyAsync(h->dIn, pin, in_span * 8, cudaMemcpyHostToDevice, h->st));
     rc = predict_core(h, method, H, h->dZ, h->dSigma, spp, mean ? h->dMean : nullptr, var ? h->dVar : nullptr,
                       cov ? h->dCov : nullptr, jac ? h->dJ : nullptr);
     if (rc) return rc;
-    double* po = pin + nz + ns;
-    if (mean) CUDA_TRY(cudaMemcpyAsync(po, h->dMean, nm * 8, cudaMemcpyDeviceToHost, h->st));
-    if (var) CUDA_TRY(cudaMemcpyAsync(po + nm, h->dVar, nm * 8, cudaMemcpyDeviceToHost, h->st));
-    if (jac) CUDA_TRY(cudaMemcpyAsync(po + 2 * nm, h->dJ, nj * 8, cudaMemcpyDeviceToHost, h->st));
-    if (cov) CUDA_TRY(cudaMemcpyAsync(po + 2 * nm + nj, h->dCov, nc * 8, cudaMemcpyDeviceToHost, h->st));
+    double* po = pin + in_span;
+    if (out_span) CUDA_TRY(cudaMemcpyAsync(po, h->dOut + lo, out_span * 8, cudaMemcpyDeviceToHost, h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
     { int prc = peer_status_check(h); if (prc) return prc; }
-    if (mean) memcpy(mean, po, nm * 8);
-    if (var) memcpy(var, po + nm, nm * 8);
-    if (jac) memcpy(jac, po + 2 * nm, nj * 8);
-    if (cov) memcpy(cov, po + 2 * nm + nj, nc * 8);
+    if (mean) memcpy(mean, po + (0 - lo), nm * 8);
+    if (var) memcpy(var, po + (off_var - lo), nm * 8);
+    if (jac) memcpy(jac, po + (off_j - lo), nj * 8);
+    if (cov) memcpy(cov, po + (off_c - lo), nc * 8);
     return GPMPC_OK;
 }
 
@@ -1262,7 +1267,11 @@ extern "C" int gpmpc_peer_export(gpmpc_handle_t h, int Hcap, void* handle64)
     h->peerHcap = Hcap;
     ALLOC(h->dPeerBlock, 2 * GPMPC_MAXW + 2 * h->peerGsz);
     ALLOC(h->dPeerCounter, 1);
-    if (!h->dPeerStatus) ALLOC(h->dPeerStatus, 1);
+    if (!h->dPeerStatus) {     // status word in mapped pinned host memory: the host reads it without a copy
+        CUDA_TRY(cudaHostAlloc((void**)&h->hPeerStatus, sizeof(int), cudaHostAllocMapped));
+        *h->hPeerStatus = 0;
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->dPeerStatus, h->hPeerStatus, 0));
+    }
     CUDA_TRY(cudaStreamSynchronize(h->st));
     cudaIpcMemHandle_t mh;
     CUDA_TRY(cudaIpcGetMemHandle(&mh, h->dPeerBlock));

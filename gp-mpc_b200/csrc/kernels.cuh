@@ -690,7 +690,7 @@ __global__ void assemble_kernel(const double* __restrict__ G, int Ny, int Nx, in
             do {
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + tid) : "memory");
                 if (v >= step) break;
-                if (clock64() - t0 > 8000000000LL) { atomicExch(status, 1 + tid); break; }   // ~4 s
+                if (clock64() - t0 > 8000000000LL) { *reinterpret_cast<volatile int*>(status) = 1 + tid; break; }   // ~4 s; status lives in mapped host memory
             } while (true);
         }
         __syncthreads();
