@@ -296,53 +296,71 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
     }
     __syncthreads();
 
-    // ---------------- Cholesky, right-looking, nb = 16 ----------------
-    for (int kb = 0; kb < 8; ++kb) {
-        const int c0 = kb * LF_NB;
-        double* Dinv = DinvAll + kb * 16 * 17;
-        if (warp == 0) warp_potrf16_trtri16(S + c0 * LF_LD + c0, Dinv, info + blockIdx.x, info_base + c0, lane);
-        __syncthreads();
-        const int nbel = LEAF_N - c0 - LF_NB;                  // rows below the diagonal block
-        {   // panel: P[r][j] = sum_{k<=j} A[r][c0+k] * Dinv[j][k]; two threads per row (8 columns each)
-            const int rr = tid >> 1, half = tid & 1;
-            double a[16];
-            if (rr < nbel) {
-                const double* src = S + (c0 + LF_NB + rr) * LF_LD + c0;
+    // ---------------- Cholesky, right-looking, nb = 16, with look-ahead ----------------
+    // After the panel of step kb only the next block column is updated by everyone (C1); then warp 0
+    // factorises + inverts the next diagonal block WHILE warps 1..7 finish the trailing update (C2).
+    auto panel = [&](int c0, const double* Dinv) {
+        // P[r][j] = sum_{k<=j} A[r][c0+k] * Dinv[j][k]; two threads per row (8 columns each)
+        const int nbel = LEAF_N - c0 - LF_NB;
+        const int rr = tid >> 1, half = tid & 1;
+        double a[16];
+        if (rr < nbel) {
+            const double* src = S + (c0 + LF_NB + rr) * LF_LD + c0;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) a[k] = src[k];
-            }
-            __syncwarp();
-            if (rr < nbel) {
-                double* dst = S + (c0 + LF_NB + rr) * LF_LD + c0;
+            for (int k = 0; k < 16; ++k) a[k] = src[k];
+        }
+        __syncwarp();
+        if (rr < nbel) {
+            double* dst = S + (c0 + LF_NB + rr) * LF_LD + c0;
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int j = half * 8 + jj;
-                    double sacc = 0.0;
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = half * 8 + jj;
+                double sacc = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) if (k <= j) sacc = fma(a[k], Dinv[j * 17 + k], sacc);
-                    dst[j] = sacc;
-                }
+                for (int k = 0; k < 16; ++k) if (k <= j) sacc = fma(a[k], Dinv[j * 17 + k], sacc);
+                dst[j] = sacc;
             }
         }
+    };
+    auto update_tile = [&](int c0, int ti, int tj) {      // C(8x8 at tile ti,tj of the trailing block) -= P_R P_C^T
+        const int R0 = c0 + LF_NB + 8 * ti, C0 = c0 + LF_NB + 8 * tj;
+        double* cp = S + (R0 + g) * LF_LD + C0 + 2 * t;
+        double acc0 = cp[0], acc1 = cp[1];
+        const double* pa = S + (R0 + g) * LF_LD + c0 + t;
+        const double* pb = S + (C0 + g) * LF_LD + c0 + t;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) dmma884(acc0, acc1, -pa[kk * 4], pb[kk * 4]);
+        cp[0] = acc0; cp[1] = acc1;
+    };
+    if (warp == 0) warp_potrf16_trtri16(S, DinvAll, info + blockIdx.x, info_base, lane);
+    __syncthreads();
+    panel(0, DinvAll);
+    __syncthreads();
+    for (int kb = 0; kb < 7; ++kb) {
+        const int c0 = kb * LF_NB, b0 = c0 + LF_NB;
+        const int nt8 = (LEAF_N - b0) >> 3;
+        // C1: the two 8-wide tile columns of the next block column
+        for (int tl = warp; tl < 2 * nt8; tl += 8) {
+            const int ti = tl >> 1, tj = tl & 1;
+            if (tj <= ti) update_tile(c0, ti, tj);
+        }
         __syncthreads();
-        {   // trailing update on 8x8 tiles of the lower triangle: C -= P_R P_C^T  (DMMA)
-            const int nt8 = nbel >> 3;
-            const int ntile = nt8 * (nt8 + 1) / 2;
-            for (int tl = warp; tl < ntile; tl += 8) {
+        if (warp == 0) {
+            warp_potrf16_trtri16(S + b0 * LF_LD + b0, DinvAll + (kb + 1) * 16 * 17, info + blockIdx.x, info_base + b0, lane);
+        } else {
+            // C2: tiles 2 <= tj <= ti < nt8 on warps 1..7
+            const int m = nt8 - 2;
+            const int ntile = m > 0 ? m * (m + 1) / 2 : 0;
+            for (int tl = warp - 1; tl < ntile; tl += 7) {
                 int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
                 while (ti * (ti + 1) / 2 > tl) --ti;
                 while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
                 const int tj = tl - ti * (ti + 1) / 2;
-                const int R0 = c0 + LF_NB + 8 * ti, C0 = c0 + LF_NB + 8 * tj;
-                double* cp = S + (R0 + g) * LF_LD + C0 + 2 * t;
-                double acc0 = cp[0], acc1 = cp[1];
-                const double* pa = S + (R0 + g) * LF_LD + c0 + t;
-                const double* pb = S + (C0 + g) * LF_LD + c0 + t;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) dmma884(acc0, acc1, -pa[kk * 4], pb[kk * 4]);
-                cp[0] = acc0; cp[1] = acc1;
+                update_tile(c0, ti + 2, tj + 2);
             }
         }
+        __syncthreads();
+        panel(b0, DinvAll + (kb + 1) * 16 * 17);
         __syncthreads();
     }
     for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
@@ -351,51 +369,42 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
     }
     __syncthreads();
 
-    // ---------------- triangular inverse, block column by block column, last first ----------------
-    for (int jb = 7; jb >= 0; --jb) {
-        const int c0 = jb * LF_NB;
-        const int nbel = LEAF_N - c0 - LF_NB;
-        const double* Dinv = DinvAll + jb * 16 * 17;
-        const int b0 = c0 + LF_NB;                             // first row/col of the trailing block
-        // X = L[below, c0:c0+16]
-        for (int idx = tid; idx < nbel * 16; idx += 256) Xs[(idx >> 4) * LF_XLD + (idx & 15)] = S[(b0 + (idx >> 4)) * LF_LD + c0 + (idx & 15)];
-        __syncthreads();
-        // Y = T X with T = Linv[below, below] (lower): row tile i0 uses k in [0, i0+8)
-        for (int rt = warp; rt < (nbel >> 3); rt += 8) {
-            const int i0 = rt * 8;
-            double y00 = 0.0, y01 = 0.0, y10 = 0.0, y11 = 0.0;
-            const double* ta = S + (b0 + i0 + g) * LF_LD + b0 + t;
-            for (int k0 = 0; k0 < i0 + 8; k0 += 4) {
-                const double av = ta[k0];
-                const double* xb = Xs + (k0 + t) * LF_XLD + g;
-                dmma884(y00, y01, av, xb[0]);
-                dmma884(y10, y11, av, xb[8]);
-            }
-            double* yp = Ys + (i0 + g) * LF_XLD + 2 * t;
-            yp[0] = y00; yp[1] = y01; yp[8] = y10; yp[9] = y11;
+    // ---------------- triangular inverse by recursive doubling ----------------
+    // the 16x16 diagonal inverses are known; for s = 16, 32, 64 every aligned pair of inverted
+    // blocks [A^-1 (p..p+s), C^-1 (p+s..p+2s)] is completed with  X = -C^-1 (B A^-1)  written over
+    // B = L[p+s.., p..] in place: 3 levels x 2 DMMA products instead of 8 sequential block columns
+    {
+        const int r = tid >> 4, c = tid & 15;               // 16 x 16 threads
+        for (int kb = 0; kb < 8; ++kb)                      // exact zeros above the diagonal: DMMA k-ranges read them
+            S[(kb * 16 + r) * LF_LD + kb * 16 + c] = (c <= r) ? DinvAll[kb * 16 * 17 + r * 17 + c] : 0.0;
+    }
+    __syncthreads();
+    double* T1 = Xs;                                        // [pairs][s][s+4], at most 4096+ doubles (Xs and Ys are adjacent)
+    for (int sz = 16; sz < LEAF_N; sz <<= 1) {
+        const int npair = LEAF_N / (2 * sz), t8 = sz >> 3, ldt = sz + 4;
+        const int ntile = npair * t8 * t8;
+        // T1 = B * Ainv   (Ainv lower: k >= j)
+        for (int tl = warp; tl < ntile; tl += 8) {
+            const int pr = tl / (t8 * t8), ti = (tl / t8) % t8, tj = tl % t8;
+            const int p0 = pr * 2 * sz;
+            const double* pa = S + (p0 + sz + 8 * ti + g) * LF_LD + p0 + t;            // B rows
+            const double* pb = S + (p0 + t) * LF_LD + p0 + 8 * tj + g;                 // Ainv[k][n]
+            double a0 = 0.0, a1 = 0.0;
+            for (int k0 = 8 * tj; k0 < sz; k0 += 4) dmma884(a0, a1, pa[k0], pb[k0 * LF_LD]);
+            double* tp = T1 + pr * sz * ldt + (8 * ti + g) * ldt + 8 * tj + 2 * t;
+            tp[0] = a0; tp[1] = a1;
         }
         __syncthreads();
-        {   // Linv[below, c0+j] = - sum_{k>=j} Y[.,k] Dinv[k][j]; two threads per row
-            const int rr = tid >> 1, half = tid & 1;
-            if (rr < nbel) {
-                double yv[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) yv[k] = Ys[rr * LF_XLD + k];
-                double* dst = S + (b0 + rr) * LF_LD + c0;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int j = half * 8 + jj;
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) if (k >= j) sacc = fma(yv[k], Dinv[k * 17 + j], sacc);
-                    dst[j] = -sacc;
-                }
-            }
-        }
-        // diagonal block of the inverse (exact zeros above its diagonal: later DMMA k-ranges read them)
-        if (tid < 256) {
-            const int r = tid >> 4, c = tid & 15;
-            S[(c0 + r) * LF_LD + c0 + c] = (c <= r) ? Dinv[r * 17 + c] : 0.0;
+        // X = -Cinv * T1  (Cinv lower: k <= i), written over B
+        for (int tl = warp; tl < ntile; tl += 8) {
+            const int pr = tl / (t8 * t8), ti = (tl / t8) % t8, tj = tl % t8;
+            const int p0 = pr * 2 * sz;
+            const double* pa = S + (p0 + sz + 8 * ti + g) * LF_LD + p0 + sz + t;       // Cinv rows
+            const double* pb = T1 + pr * sz * ldt + t * ldt + 8 * tj + g;              // T1[k][n]
+            double a0 = 0.0, a1 = 0.0;
+            for (int k0 = 0; k0 < 8 * ti + 8; k0 += 4) dmma884(a0, a1, -pa[k0], pb[k0 * ldt]);
+            double* xp = S + (p0 + sz + 8 * ti + g) * LF_LD + p0 + 8 * tj + 2 * t;
+            xp[0] = a0; xp[1] = a1;
         }
         __syncthreads();
     }
