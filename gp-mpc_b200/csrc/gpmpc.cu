@@ -82,9 +82,6 @@ struct gpmpc_handle_s {
     // nlml scratch
     double *dU = nullptr, *dKinv = nullptr, *dGradPart = nullptr, *dGrad = nullptr;
     bool has_data = false, has_hyper = false, factorized = false;
-    // CUDA-graph cache of the host predict path (single GPU): H2D + 5 kernels + D2H become one launch
-    struct GraphEntry { int method, H, spp, flags, refine, ksplit; size_t lo, span, in_span; double* pin; cudaGraphExec_t exec; };
-    GraphEntry graphs[4] = {}; int ngraphs = 0, graph_next = 0; int opt_graphs = 1; unsigned long long model_epoch = 0, graph_epoch = 0;
     // EM scratch
     double *dKinvAll = nullptr, *dEMP = nullptr, *dEmE = nullptr, *dEmF = nullptr, *dEmW = nullptr, *dEmIJ = nullptr;
     double *dEmMeanPart = nullptr, *dEmPart = nullptr;
@@ -427,7 +424,6 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
     if (h->hPinned) cudaFreeHost(h->hPinned);
-    for (int gi = 0; gi < h->ngraphs; ++gi) if (h->graphs[gi].exec) cudaGraphExecDestroy(h->graphs[gi].exec);
     for (int d = 0; d < MAX_DEPTH; ++d) {
         if (h->sideSt[d]) { cudaStreamSynchronize(h->sideSt[d]); cudaStreamDestroy(h->sideSt[d]); }
         if (h->evA[d]) cudaEventDestroy(h->evA[d]);
@@ -446,7 +442,7 @@ static int ensure_pinned(gpmpc_handle_t h, size_t bytes)
     if (h->hPinned) cudaFreeHost(h->hPinned);
     h->hPinned = nullptr; h->hPinnedBytes = 0;
     CUDA_TRY(cudaMallocHost((void**)&h->hPinned, bytes));
-    h->hPinnedBytes = bytes; h->model_epoch++;
+    h->hPinnedBytes = bytes;
     return GPMPC_OK;
 }
 
@@ -573,7 +569,7 @@ extern "C" int gpmpc_factorize(gpmpc_handle_t h, double jitter, int* info)
     CUDA_TRY(cudaMemcpyAsync(res.data(), h->dRes, 2 * nl * 8, cudaMemcpyDeviceToHost, h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
     for (int a = 0; a < nl; ++a) { h->logdet[a] = res[2 * a]; h->yalpha[a] = res[2 * a + 1]; }
-    h->factorized = true; h->em_kinv_valid = false; h->model_epoch++;
+    h->factorized = true; h->em_kinv_valid = false;
     return GPMPC_OK;
 }
 
@@ -668,7 +664,6 @@ extern "C" int gpmpc_get(gpmpc_handle_t h, int what, int a, double* dst)
 extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value)
 {
     if (!h || !name) return GPMPC_ERR_ARG;
-    h->model_epoch++;          // any option may change the captured launch sequence
     if (!strcmp(name, "refine")) { h->opt_refine = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "ksplit")) {
         const int v = (int)value;
@@ -677,7 +672,6 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
     }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "tri_variant")) { h->opt_tri_variant = (int)value; return GPMPC_OK; }
-    if (!strcmp(name, "graphs")) { h->opt_graphs = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "small_tiles")) { h->opt_small_tiles = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "peer")) { h->opt_peer = value != 0.0; return GPMPC_OK; }
@@ -716,7 +710,7 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
         h->dZ = h->dIn; h->dSigma = h->dIn + cap * Nx;
         h->dMean = h->dOut; h->dVar = h->dOut + cap * Ny; h->dJ = h->dOut + 2 * cap * Ny;
         h->dCov = h->dOut + 2 * cap * Ny + cap * Ny * Nx;
-        h->Hcap = (int)cap; h->model_epoch++;
+        h->Hcap = (int)cap;
     }
     return GPMPC_OK;
 }
@@ -1122,56 +1116,12 @@ extern "C" int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* 
     double* pin = h->hPinned;
     memcpy(pin, Z, nz * 8);
     if (ns) memcpy(pin + cap * Nx, Sigma, ns * 8);
+    CUDA_TRY(cudaMemcpyAsync(h->dIn, pin, in_span * 8, cudaMemcpyHostToDevice, h->st));
+    rc = predict_core(h, method, H, h->dZ, h->dSigma, spp, mean ? h->dMean : nullptr, var ? h->dVar : nullptr,
+                      cov ? h->dCov : nullptr, jac ? h->dJ : nullptr);
+    if (rc) return rc;
     double* po = pin + in_span;
-    const int flags = (mean ? 1 : 0) | (var ? 2 : 0) | (cov ? 4 : 0) | (jac ? 8 : 0);
-    bool launched = false;
-    if (h->opt_graphs && h->world == 1) {
-        // single-GPU: replay the whole call (H2D, kernels, D2H) as one CUDA graph once the same
-        // shape has been seen; the first call of a shape runs eagerly (it also configures kernels)
-        if (h->graph_epoch != h->model_epoch) {
-            for (int gi = 0; gi < h->ngraphs; ++gi) if (h->graphs[gi].exec) cudaGraphExecDestroy(h->graphs[gi].exec);
-            h->ngraphs = 0; h->graph_next = 0; h->graph_epoch = h->model_epoch;
-        }
-        int hit = -1;
-        for (int gi = 0; gi < h->ngraphs; ++gi) {
-            const auto& ge = h->graphs[gi];
-            if (ge.method == method && ge.H == H && ge.spp == spp && ge.flags == flags && ge.lo == lo && ge.span == out_span &&
-                ge.in_span == in_span && ge.pin == pin) { hit = gi; break; }
-        }
-        if (hit >= 0 && h->graphs[hit].exec) {
-            CUDA_TRY(cudaGraphLaunch(h->graphs[hit].exec, h->st));
-            launched = true;
-        } else if (hit >= 0) {          // second sighting: capture
-            cudaGraph_t graph = nullptr;
-            CUDA_TRY(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
-            cudaError_t e1 = cudaMemcpyAsync(h->dIn, pin, in_span * 8, cudaMemcpyHostToDevice, h->st);
-            int rcc = predict_core(h, method, H, h->dZ, h->dSigma, spp, mean ? h->dMean : nullptr, var ? h->dVar : nullptr,
-                                   cov ? h->dCov : nullptr, jac ? h->dJ : nullptr);
-            cudaError_t e2 = out_span ? cudaMemcpyAsync(po, h->dOut + lo, out_span * 8, cudaMemcpyDeviceToHost, h->st) : cudaSuccess;
-            cudaError_t e3 = cudaStreamEndCapture(h->st, &graph);
-            if (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && rcc == GPMPC_OK && graph &&
-                cudaGraphInstantiate(&h->graphs[hit].exec, graph, 0) == cudaSuccess) {
-                CUDA_TRY(cudaGraphLaunch(h->graphs[hit].exec, h->st));
-                launched = true;
-            } else {
-                h->graphs[hit].exec = nullptr;
-                h->opt_graphs = 0;       // capture is not usable here: stay on the eager path
-                cudaGetLastError();
-            }
-            if (graph) cudaGraphDestroy(graph);
-        } else {                         // first sighting: remember the shape, run eagerly
-            int slot = (h->ngraphs < 4) ? h->ngraphs++ : (h->graph_next++ & 3);
-            if (h->graphs[slot].exec) cudaGraphExecDestroy(h->graphs[slot].exec);
-            h->graphs[slot] = {method, H, spp, flags, h->opt_refine, h->opt_ksplit, lo, out_span, in_span, pin, nullptr};
-        }
-    }
-    if (!launched) {
-        CUDA_TRY(cudaMemcpyAsync(h->dIn, pin, in_span * 8, cudaMemcpyHostToDevice, h->st));
-        rc = predict_core(h, method, H, h->dZ, h->dSigma, spp, mean ? h->dMean : nullptr, var ? h->dVar : nullptr,
-                          cov ? h->dCov : nullptr, jac ? h->dJ : nullptr);
-        if (rc) return rc;
-        if (out_span) CUDA_TRY(cudaMemcpyAsync(po, h->dOut + lo, out_span * 8, cudaMemcpyDeviceToHost, h->st));
-    }
+    if (out_span) CUDA_TRY(cudaMemcpyAsync(po, h->dOut + lo, out_span * 8, cudaMemcpyDeviceToHost, h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
     { int prc = peer_status_check(h); if (prc) return prc; }
     if (mean) memcpy(mean, po + (0 - lo), nm * 8);
@@ -1221,7 +1171,7 @@ extern "C" int gpmpc_append(gpmpc_handle_t h, const double* x_new, const double*
             return GPMPC_ERR_NOTPD;
         }
     h->N = N + 1;
-    h->em_kinv_valid = false; h->model_epoch++;
+    h->em_kinv_valid = false;
     rc = launch_alpha(h, 0, nl);
     if (rc) return rc;
     std::vector<double> res(2 * nl);
