@@ -285,8 +285,7 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
 {
     extern __shared__ __align__(16) double S[];                // [128][132]
     double* DinvAll = S + LEAF_N * LF_LD;                      // [8][16][17]
-    double* Xs = DinvAll + 8 * 16 * 17;                        // [128][20]
-    double* Ys = Xs + LEAF_N * LF_XLD;                         // [128][20]
+    double* Xs = DinvAll + 8 * 16 * 17;                        // scratch for the inverse assembly (2 x 128 x 20 doubles)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     double* Ab = A + (long long)blockIdx.x * sA;
     double* Lb = Li + (long long)blockIdx.x * sLi;
