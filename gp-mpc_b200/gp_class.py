@@ -196,7 +196,7 @@ class GP:
         rows = train_gp_b200(self.__engine, self.__X, self.__Y, meanFunc=self.__mean_func,
                              optimizer_opts=opts, multistart=multistart, hyper_init=hyp_init)
         blocks = self.__comm.allgather_object((self.__engine.out_begin, rows))
-        hyper = np.zeros((self.__Ny, self.__Nx + 2))
+        hyper = np.zeros((self.__Ny, blocks[0][1].shape[1]))      # Nx+2 (+ mean parameters, all zero)
         for b, r in blocks:
             hyper[b:b + len(r)] = r
         self.__hyper = hyper

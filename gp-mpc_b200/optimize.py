@@ -56,10 +56,13 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
     (shape (out_count, Nx+2)) -- the caller gathers them across ranks."""
     from scipy.optimize import minimize
 
-    if count_mean_params(meanFunc, X.shape[1]) != 0:
-        raise NotImplementedError(
-            "mean function %r: the reference's numeric path itself supports the zero mean only "
-            "(optimize.py:377-379); non-zero prior means are a SURVEY 8f 'next' row" % meanFunc)
+    # 'const' / 'linear' / 'polynomial' add h_m mean parameters to every hyper row
+    # (optimize.py:402-417).  In the reference's NUMERIC path (the default, and the one mirrored
+    # here) the objective ignores them (calc_NLL_numpy reads hyper[:Nx+2] only, optimize.py:337-340;
+    # "only support a zero-mean function", :377-379), their bounds are set after `bounds` was built
+    # (:435-460) and therefore never reach SLSQP, so they stay at their initial value 0 and the
+    # fitted prior mean is identically zero.  That behaviour is reproduced: zero columns.
+    h_m = count_mean_params(meanFunc, X.shape[1])
     N, Nx = X.shape
     options = {'disp': False, 'maxiter': 10000}
     jac_mode = 'analytic'
@@ -76,7 +79,7 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
         print('\n________________________________________')
         print('# Optimizing hyperparameters (N=%d)' % N)
         print('----------------------------------------')
-    rows = np.zeros((engine.out_count, Nx + 2))
+    rows = np.zeros((engine.out_count, Nx + 2 + h_m))
     for k, a in enumerate(engine.local_outputs):
         bounds, init = bounds_and_init(X, Y[:, a], fixed_bounds)
         if hyper_init is not None:
@@ -94,7 +97,7 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
                        bounds=bounds, tol=1e-12)
         if verbose:
             print("* State %d:  %f s" % (a, time.time() - t0))
-        rows[k] = res.x
+        rows[k, :Nx + 2] = res.x
     if verbose:
         print('----------------------------------------')
     return rows

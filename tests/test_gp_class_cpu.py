@@ -1,0 +1,90 @@
+"""Host-side behaviour of the GP class (constructor paths, standardisation quirks, JSON schema,
+error types, mean-function bookkeeping) exercised on CPU through the oracle-backed stand-in
+engine (tests/_fake_engine.py).  The arithmetic itself is covered by the -m gpu tests."""
+import json
+
+import numpy as np
+import pytest
+
+import gp_mpc_b200
+from oracle import gp_oracle as orc
+from tests._fake_engine import OracleEngine
+from tests._util import load_fixture, load_golden, relinf
+
+
+def _gp(name, **kw):
+    m = load_fixture(name)
+    args = dict(mean_func='zero', gp_method='TA', normalize=m['normalize'], hyper=dict(hyper=m['hyper']),
+                engine_factory=OracleEngine)
+    if m['normalize']:
+        args.update(meta=m['meta'], xlb=m['xlb'], xub=m['xub'], ulb=m['ulb'], uub=m['uub'])
+    args.update(kw)
+    return gp_mpc_b200.GP(m['X'], m['Y'], **args), m
+
+
+@pytest.mark.parametrize('name', ['tank', 'car'])
+def test_predict_wrapper_follows_the_reference(name):
+    """gp_class.py:245-263: x,u standardised, mean de-standardised, covariance NOT rescaled."""
+    gp, m = _gp(name)
+    d = load_golden('derived', name)
+    tol = 1e-8 if name == 'tank' else 1e-6       # car: cond(K) ~ 1e10, factors are recomputed from (X, hyper)
+    mean, cov = gp.predict(d['x0'], d['u0'], d['Sigma'])
+    assert relinf(mean, d['mean_ta']) < tol and relinf(cov, d['cov_ta']) < tol
+    assert mean.shape == (m['Y'].shape[1], 1)
+    gp.set_method('ME')
+    mean, cov = gp.predict(d['x0'], d['u0'], None)
+    assert relinf(cov, d['cov_me']) < tol
+    A, B = gp.discrete_linearize(d['x0'], d['u0'], d['Sigma'])
+    assert relinf(A, d['A']) < tol and relinf(B, d['B']) < tol
+    with pytest.raises(NameError):
+        gp.set_method('XY')
+    with pytest.raises(NotImplementedError):
+        gp.set_method('old_ME')
+
+
+def test_json_schema_and_hyper_views(tmp_path):
+    gp, m = _gp('tank')
+    hp = gp.get_hyper_parameters()
+    assert np.array_equal(hp['length_scale'], m['hyper'][:, :6])
+    assert np.allclose(hp['signal_var'], m['signal_var']) and np.allclose(hp['noise_var'], m['noise_var'])
+    assert np.array_equal(hp['mean'], m['hyper'][:, 7:])            # includes sn as first column (q1)
+    gp.save_model(str(tmp_path / 'mdl'))
+    dd = json.load(open(str(tmp_path / 'mdl') + '.json'))
+    assert set(dd) == {'X', 'Y', 'hyper', 'mean_func', 'normalize', 'xlb', 'xub', 'ulb', 'uub', 'meta'}
+    assert set(dd['meta']) == {'meanY', 'stdY', 'meanZ', 'stdZ', 'meanX', 'stdX', 'meanU', 'stdU'}
+    assert np.array_equal(np.array(dd['X']), m['X'])                # stored standardised, not re-standardised
+    gp2 = gp_mpc_b200.GP.load_model(str(tmp_path / 'mdl'), engine_factory=OracleEngine)
+    assert gp2.get_size() == gp.get_size() == (60, 4, 2)
+
+
+def test_training_statistics_and_mean_function_bookkeeping():
+    p = orc.synthetic_problem(30, 3, 2, config_id=9)
+    Xr = 5.0 + 2.0 * p['X']; Yr = -1.0 + 0.3 * p['Y']
+    gp = gp_mpc_b200.GP(Xr, Yr, normalize=True, xlb=[0, 0], xub=[1, 1], ulb=[0], uub=[1], mean_func='linear',
+                        optimizer_opts={'maxiter': 20}, engine_factory=OracleEngine)
+    # 'linear' adds Nx+1 mean parameters per output that the numeric path leaves at zero
+    hp = gp.get_hyper_parameters()
+    assert hp['mean'].shape == (2, 1 + 3 + 1) and np.all(hp['mean'][:, 1:] == 0.0)
+    st = orc.data_stats(Xr, Yr, 2)
+    d = gp._GP__to_dict()
+    for k in st:
+        assert np.allclose(d['meta'][k], st[k])
+    assert np.allclose(np.array(d['X']), (Xr - st['meanZ']) / st['stdZ'])
+    with pytest.raises(NameError):
+        gp_mpc_b200.GP(Xr, Yr, mean_func='cubic', engine_factory=OracleEngine, xlb=[0, 0], xub=[1, 1], ulb=[0], uub=[1])
+    with pytest.raises(ValueError):
+        gp_mpc_b200.GP(Xr, Yr[:-1], engine_factory=OracleEngine)
+
+
+def test_validate_matches_oracle_and_prints_banners(capsys):
+    gp, m = _gp('tank')
+    rng = np.random.default_rng(3)
+    Xt = m['meta']['meanZ'] + m['meta']['stdZ'] * rng.standard_normal((15, 6)) * 0.4
+    Yt = m['meta']['meanY'] + m['meta']['stdY'] * rng.standard_normal((15, 4)) * 0.4
+    smse, mnlp = gp.validate(Xt, Yt)
+    so, mo = orc.validate(dict(m, alpha=gp.get_alpha(), chol=gp.get_chol()), Xt, Yt)
+    assert relinf(smse, so) < 1e-9 and relinf(mnlp, mo) < 1e-9
+    out = capsys.readouterr().out
+    assert '# Validation of GP model' in out and '* Standardized mean squared error:' in out
+    gp.print_hyper_parameters()
+    assert '# Hyper-parameters' in capsys.readouterr().out
