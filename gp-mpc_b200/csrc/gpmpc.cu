@@ -89,7 +89,7 @@ struct gpmpc_handle_s {
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 3, opt_tri_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 592, opt_kbuild_occ = 4;   // 128x64-tile count below which 64x32 tiles are used
+    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 3, opt_tri_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 592;   // 128x64-tile count below which 64x32 tiles are used
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     // peer (CUDA IPC) exchange: [flags: 2*MAXW u64][gather buffer parity 0][parity 1]
@@ -259,16 +259,14 @@ static int launch_kbuild(gpmpc_handle_t h, const double* dHyp, const double* dJi
     const int KD = (h->Nx + 3) & ~3, S = ((KD >> 2) & 1) ? KD : KD + 4;
     const int smem = (2 * KB2_TILE * S + 2 * KB2_TILE + 16) * 8;
     if (!conf[h->device % GPMPC_MAX_DEVICES]) {
-        const int mx = (2 * KB2_TILE * 36 + 2 * KB2_TILE + 16) * 8;
-        CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (2 * KB2_TILE * 36 + 2 * KB2_TILE + 16) * 8));
         conf[h->device % GPMPC_MAX_DEVICES] = true;
     }
     const int T = h->Npad / KB2_TILE;
     dim3 grid(T * (T + 1) / 2, 1, batch);
-    auto kern = (h->opt_kbuild_occ >= 6) ? kbuild_dmma_kernel<6> : (h->opt_kbuild_occ == 5) ? kbuild_dmma_kernel<5> : kbuild_dmma_kernel<4>;
-    kern<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dMu, dHyp, h->Nx + 2, dJit, K, h->Npad, slab(h), full);
+    kbuild_dmma_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dMu, dHyp, h->Nx + 2, dJit,
+                                                    K, h->Npad, slab(h), full);
     CUDA_TRY(cudaGetLastError());
     return GPMPC_OK;
 }
@@ -674,7 +672,6 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
     }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "tri_variant")) { h->opt_tri_variant = (int)value; return GPMPC_OK; }
-    if (!strcmp(name, "kbuild_occ")) { h->opt_kbuild_occ = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "small_tiles")) { h->opt_small_tiles = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "peer")) { h->opt_peer = value != 0.0; return GPMPC_OK; }

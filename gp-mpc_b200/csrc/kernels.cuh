@@ -52,8 +52,7 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
 }
 
 #define KB2_TILE 128
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB)
+__global__ void __launch_bounds__(256)
 kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const double* __restrict__ mu,
                    const double* __restrict__ hyp, int hyp_ld, const double* __restrict__ jitter,
                    double* __restrict__ K, int ld, long long sK, int full)
