@@ -37,6 +37,7 @@ WORKLOADS = {
     'c2': dict(N=1000, Nx=8, Ny=6, H=30, cfg=2, name='C2: N=1000 Nx=8 Ny=6 H=30 TA'),
 }
 METRIC = 'GP predictions/sec (N train x horizon test, fp64)'
+PREDICT_KERNEL_NAME = 'gemm_dmma_tmap_kernel<BM,128,1,8,4,2> (v = Linv ks: DMMA fed by TMA tensor maps, split-K, longest-first)'
 
 
 def make_workload(N, Nx, Ny, cfg, H):
@@ -127,37 +128,57 @@ def cpu_predict_port(orc, X, hyper_a, alpha_a, L_a, Z):
 
 def run_reference(args, wl, rank):
     """--impl reference: the reference's own CPU path for this metric (oracle port; the
-    reference is pure Python on numpy/CasADi, CasADi is not installable here), all host
-    threads, bounded sample: ONE of the Ny outputs factorised and predicted on the CPU, the
-    other outputs cost the same, so predictions/s = H / (Ny * t_one_output)."""
+    reference is pure Python on numpy/CasADi, CasADi is not installable here) on all host
+    threads, at the SAME configuration as the GPU arm: every one of the Ny outputs is
+    factorised on the CPU (set-up, not timed -- as in the GPU arm) and every timed step
+    predicts all H points for all Ny outputs (ks, mean, L\\ks, var, Jacobian, TA covariance).
+    Falls back to a stated sub-sample (1 output, time x Ny) only when the host cannot hold
+    Ny factors or one CPU factorisation takes longer than 60 s."""
     if rank != 0:
         return
     from oracle import gp_oracle as orc
     N, Nx, Ny, H = wl['N'], wl['Nx'], wl['Ny'], wl['H']
-    Ns = N if N <= 8192 else 8192       # bounded: CPU potrf at 16384 alone is ~1 min on few cores
-    w = make_workload(Ns, Nx, Ny, wl['cfg'], H)
+    w = make_workload(N, Nx, Ny, wl['cfg'], H)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64e9
+    n_fac = Ny if avail > (Ny + 3) * 8.0 * N * N else 1
+    facs = []
     t0 = time.perf_counter()
-    K = orc.covSEard_blas(w['X'], w['X'], w['hyper'][0, :Nx], w['hyper'][0, Nx] ** 2)
-    K[np.diag_indices(Ns)] += w['hyper'][0, Nx + 1] ** 2
-    L = np.linalg.cholesky(K)
-    from scipy.linalg import solve_triangular
-    alpha = solve_triangular(L.T, solve_triangular(L, w['Y'][:, 0], lower=True), lower=False)
+    for a in range(n_fac):
+        t1 = time.perf_counter()
+        facs.append(orc.factor_large(w['X'], w['Y'][:, a], w['hyper'][a]))
+        if a == 0 and time.perf_counter() - t1 > 60.0:
+            break
+    n_fac = len(facs)
     t_setup = time.perf_counter() - t0
+
+    def step():
+        mean = np.zeros((H, n_fac)); var = np.zeros((H, n_fac)); J = np.zeros((H, n_fac, Nx))
+        for a in range(n_fac):
+            mean[:, a], var[:, a], J[:, a] = cpu_predict_port(orc, w['X'], w['hyper'][a], facs[a]['alpha'], facs[a]['chol'], w['Z'])
+        return mean, orc.ta_cov(var, J, w['Sigma'])
+
     for _ in range(args.warmup):
-        cpu_predict_port(orc, w['X'], w['hyper'][0], alpha, L, w['Z'])
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_predict_port(orc, w['X'], w['hyper'][0], alpha, L, w['Z'])
+        step()
     dt = (time.perf_counter() - t0) / args.steps
-    scale = (N / Ns) ** 2                # predict cost is O(N^2) per test point (triangular solve)
-    t_step = dt * Ny * scale
+    t_step = dt * (Ny / n_fac)
     val = H / t_step
-    sample = ('1 of %d outputs, N=%d%s, H=%d; per-step time x Ny%s; CPU setup (K+potrf) %.1fs not timed'
-              % (Ny, Ns, '' if Ns == N else ' (of %d)' % N, H, '' if Ns == N else ' x (N/Ns)^2', t_setup))
+    if n_fac == Ny:
+        sample = ('full configuration: all %d outputs at N=%d, H=%d per step; CPU set-up (K + potrf + alpha, %d outputs) '
+                  '%.1f s not timed' % (Ny, N, H, Ny, t_setup))
+    else:
+        sample = ('%d of %d outputs at full N=%d, H=%d; per-step time x %g (outputs are independent); CPU set-up %.1f s '
+                  'not timed' % (n_fac, Ny, N, H, Ny / n_fac, t_setup))
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'predictions/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_step * 1e3, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': wl['name']},
+            'config': {'workload': wl['name'], 'method': 'TA', 'N': N, 'Nx': Nx, 'Ny': Ny, 'H': H},
             'cpu_baseline': {'value': val, 'unit': 'predictions/s', 'cores': os.cpu_count(), 'kind': 'port',
                              'sample': sample},
             'e2e': {'value': val, 'unit': 'predictions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -233,6 +254,14 @@ def main():
                 eng.set_option('peer', 0)
     else:
         peer_mode = False
+    # north-star kernel targets, timed with CUDA events inside the library on this engine's slabs
+    # (they are scratch until factorize): K build, the top-level trailing update, potrf+trtri
+    sec = {}
+    if os.environ.get('GPMPC_BENCH_SECONDARY', '1') == '1':
+        sec['kbuild_full_ms'] = eng.profile(L.PROF_KBUILD_FULL, reps=10)
+        sec['kbuild_lower_ms'] = eng.profile(L.PROF_KBUILD_LOWER, reps=10)
+        sec['syrk_ms'] = eng.profile(L.PROF_SYRK, n=0, reps=3)
+        sec['factorize_ms'] = eng.profile(L.PROF_FACTORIZE, reps=2)
     eng.factorize()
     t_setup = time.perf_counter() - t0
 
@@ -302,7 +331,8 @@ def main():
     ms_tri = eng.profile(L.PROF_TRIGEMM, n=H, reps=max(5, args.steps))
     flops = n * H * float(N) * N
     achieved = flops / (ms_tri * 1e-3) / 1e12
-    # fp64 tensor peak is not in MEASURED_PEAKS.json (bf16 only): measure cuBLAS DGEMM here
+    # fp64 tensor peak is not in MEASURED_PEAKS.json (bf16 only): measure cuBLAS DGEMM here, as a
+    # burst (best of 4, for kernels timed alone) and sustained (back to back for ~4 s, clocks sampled)
     a = torch.randn(8192, 8192, dtype=torch.float64, device='cuda'); bmat = torch.randn_like(a)
     best = 1e9
     for _ in range(4):
@@ -310,6 +340,18 @@ def main():
         e0.record(); torch.matmul(a, bmat); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     dgemm_tf = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+    sustained = None
+    if rank == 0 and os.environ.get('GPMPC_BENCH_SUSTAINED', '1') == '1':
+        n_it = max(8, int(4000.0 / best))
+        smp = ClockSampler(local_rank); smp.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_it):
+            torch.matmul(a, bmat)
+        e1.record(); torch.cuda.synchronize()
+        ck = smp.stop()
+        sustained = {'tflops': 2 * 8192.0 ** 3 * n_it / (e0.elapsed_time(e1) * 1e-3) / 1e12, 'iters': n_it,
+                     'seconds': e0.elapsed_time(e1) * 1e-3, 'clocks': ck}
     del a, bmat
     peaks = {}
     try:
@@ -317,39 +359,102 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    hbm_src = 'MEASURED_PEAKS.json (measured)' if peaks else 'fallback 6650 GB/s'
     traffic = None
+    tj = {}
     try:      # per-launch DRAM bytes from the committed ncu capture (profiles/), same workload only
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
         if N == 16384 and H == 50:
             traffic = n * tj['trigemm_N16384_H50_per_output_bytes']
     except Exception:
         pass
-    roofline = {'bound': 'tensor', 'kernel': 'gemm_dmma_tmap_kernel<BM,128,1,8,4,2> (v = Linv ks: DMMA fed by TMA tensor maps, split-K, longest-first)',
+    roofline = {'bound': 'tensor', 'kernel': PREDICT_KERNEL_NAME,
                 'achieved': achieved, 'peak': dgemm_tf, 'unit': 'TFLOP/s', 'frac': achieved / dgemm_tf,
-                'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (fp64 is absent from MEASURED_PEAKS.json)',
+                'peak_source': 'cuBLAS DGEMM 8192^3 burst (best of 4) measured in this run; fp64 is absent from MEASURED_PEAKS.json',
+                'peak_sustained': sustained, 'frac_vs_sustained': (achieved / sustained['tflops']) if sustained else None,
                 'ms_per_launch': ms_tri, 'traffic': traffic, 'algorithmic_bytes': n * 4.0 * N * N,
                 'hbm_view': {'algorithmic_gbs': n * 4.0 * N * N / (ms_tri * 1e-3) / 1e9, 'peak_gbs': hbm_peak,
-                             'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}}
-
-    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ---------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import gp_oracle as orc
-        t0 = time.perf_counter()
-        La = eng.get(L.GET_CHOL, b)           # factor computed on the GPU: the CPU leg times predict only
-        al = eng.get(L.GET_ALPHA, b)
-        reps = 0; tt = 0.0
-        while tt < 10.0 and reps < 5:
+                             'peak_source': hbm_src}}
+    # secondary kernels (BASELINE north_star targets: >=0.70 HBM on the K build, >=0.80 tensor on the
+    # Cholesky trailing update), one output at this N; algorithmic work per DESIGN.md section 4
+    secondary = None
+    if sec:
+        Np = (N + 127) // 128 * 128
+        n1 = (Np // 128 // 2) * 128; n2 = Np - n1
+        syrk_flops = float(n2) * (n2 + 128) * n1              # lower tiles incl. the diagonal ones, 2 flops/MAC
+        secondary = {
+            'kbuild_full': {'ms': sec['kbuild_full_ms'], 'gbs': 8.0 * Np * Np / sec['kbuild_full_ms'] / 1e6,
+                            'frac': 8.0 * Np * Np / sec['kbuild_full_ms'] / 1e6 / hbm_peak, 'bound': 'hbm',
+                            'algorithmic_bytes': 8.0 * Np * Np, 'traffic': tj.get('kbuild_full_N16384_bytes') if N == 16384 else None,
+                            'peak_source': hbm_src},
+            'kbuild_lower': {'ms': sec['kbuild_lower_ms'], 'gbs': 4.0 * Np * (Np + 128) / sec['kbuild_lower_ms'] / 1e6,
+                             'frac': 4.0 * Np * (Np + 128) / sec['kbuild_lower_ms'] / 1e6 / hbm_peak, 'bound': 'hbm',
+                             'algorithmic_bytes': 4.0 * Np * (Np + 128)},
+            'syrk_trailing_update': {'ms': sec['syrk_ms'], 'tflops': syrk_flops / sec['syrk_ms'] / 1e9,
+                                     'frac': syrk_flops / sec['syrk_ms'] / 1e9 / dgemm_tf, 'bound': 'tensor',
+                                     'shape': 'C(%d x %d lower) -= P P^T, K=%d' % (n2, n2, n1),
+                                     'traffic': tj.get('syrk_N16384_bytes') if N == 16384 else None},
+            'factorize_potrf_trtri': {'ms': sec['factorize_ms'], 'tflops': (2.0 / 3.0) * float(Np) ** 3 / sec['factorize_ms'] / 1e9,
+                                      'frac': (2.0 / 3.0) * float(Np) ** 3 / sec['factorize_ms'] / 1e9 / dgemm_tf, 'bound': 'tensor',
+                                      'note': 'K build + potrf + explicit L^-1 of one output, 2N^3/3 flops'},
+        }
+        if rank == 0 and world == 1 and os.environ.get('GPMPC_BENCH_NLML', '1') == '1':
+            # BASELINE config C4: NLML + analytic gradient at N=8192, Nx=8 (one output) through the C ABI
+            w4 = make_workload(8192, 8, 1, 4, 1)
+            e4 = gp_mpc_b200.Engine(8192, 8, 1, 0, 1, device=local_rank)
+            e4.set_data(w4['X'], w4['Y'])
+            e4.nlml(0, w4['hyper'][0], grad=True)
             t1 = time.perf_counter()
-            cm, cv, cj = cpu_predict_port(orc, w['X'], w['hyper'][b], al, La, w['Z'])
-            tt += time.perf_counter() - t1; reps += 1
-        t_one = tt / reps
-        cpu = {'value': H / (t_one * Ny), 'unit': 'predictions/s', 'cores': os.cpu_count(), 'kind': 'port',
-               'sample': 'oracle port of the numeric predict (ks, mean, L\\ks triangular solve, var, Jacobian) for 1 of '
-                         '%d outputs at full N=%d, H=%d, %d reps, time x Ny; factor taken from the GPU' % (Ny, N, H, reps),
-               'parity_vs_gpu': {'mean': float(np.abs(cm - mean[:, b]).max() / np.abs(cm).max()),
-                                 'var': float(np.abs(cv - var[:, b]).max() / np.abs(cv).max())}}
-        del La
+            for _ in range(3):
+                e4.nlml(0, w4['hyper'][0], grad=True)
+            ms_g = (time.perf_counter() - t1) / 3 * 1e3
+            t1 = time.perf_counter()
+            for _ in range(3):
+                e4.nlml(0, w4['hyper'][0], grad=False)
+            ms_v = (time.perf_counter() - t1) / 3 * 1e3
+            e4.close()
+            secondary['nlml_c4'] = {'ms_value_and_grad': ms_g, 'ms_value_only': ms_v, 'N': 8192, 'Nx': 8,
+                                    'tflops': 8192.0 ** 3 / ms_g / 1e9, 'frac': 8192.0 ** 3 / ms_g / 1e9 / dgemm_tf,
+                                    'note': 'host-timed C-ABI call (sync inside); N^3 flops = potrf N^3/3 + trtri N^3/3 + K^-1 N^3/3'}
+
+    # ---- parity against an INDEPENDENT CPU factor (rank 0, every N) + CPU baseline (N=1) --------
+    cpu = None
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import gp_oracle as orc
+        outs = sorted({0, Ny - 1})          # rank 0's own first output and the last rank's last output
+        ref = {}
+        t_fac = 0.0
+        for a_o in outs:
+            t1 = time.perf_counter()
+            f = orc.factor_large(w['X'], w['Y'][:, a_o], w['hyper'][a_o])
+            t_fac += time.perf_counter() - t1
+            ref[a_o] = (f,) + tuple(orc.predict_large(w['X'], w['hyper'][a_o], f['alpha'], f['chol'], w['Z']))
+        def rel(x, y):
+            return float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-300))
+        pm = max(rel(mean[:, a_o], ref[a_o][1]) for a_o in outs)
+        pv = max(rel(var[:, a_o], ref[a_o][2]) for a_o in outs)
+        pj = max(rel(jac[:, a_o], ref[a_o][3]) for a_o in outs)
+        vo = np.stack([ref[a_o][2] for a_o in outs], 1); Jo = np.stack([ref[a_o][3] for a_o in outs], 1)
+        co = orc.ta_cov(vo, Jo, w['Sigma'])
+        pc = rel(cov[:, outs][:, :, outs], co)
+        parity = {'mean': pm, 'var': pv, 'jac': pj, 'cov': pc, 'max': max(pm, pv, pj, pc), 'tol': 1e-6,
+                  'ok': bool(max(pm, pv, pj, pc) < 1e-6), 'outputs_checked': outs,
+                  'how': 'independent CPU factor (np.linalg.cholesky of the expansion-form K, triangular solves) of outputs '
+                         '%s at full N=%d; gathered GPU result of the e2e call compared, batch-inf-norm relative' % (outs, N)}
+        if world == 1:
+            f0 = ref[0][0]
+            reps = 0; tt = 0.0
+            while tt < 10.0 and reps < 5:
+                t1 = time.perf_counter()
+                cpu_predict_port(orc, w['X'], w['hyper'][0], f0['alpha'], f0['chol'], w['Z'])
+                tt += time.perf_counter() - t1; reps += 1
+            t_one = tt / reps
+            cpu = {'value': H / (t_one * Ny), 'unit': 'predictions/s', 'cores': os.cpu_count(), 'kind': 'port',
+                   'sample': 'oracle port of the numeric predict (ks, mean, L\\ks triangular solve, var, Jacobian) for 1 of '
+                             '%d outputs at full N=%d, H=%d, %d reps, time x Ny; CPU factor (%.1f s per output) not timed'
+                             % (Ny, N, H, reps, t_fac / len(outs))}
+        del ref
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'predictions/s', 'n_gpus': world, 'steps': args.steps,
@@ -363,7 +468,7 @@ def main():
                 'clocks': clocks,
                 'e2e': {'value': e2e_val, 'unit': 'predictions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
                 'gpu_launches': args.steps * (4 * ((H + 63) // 64) + 1),
-                'roofline': roofline, 'cpu_baseline': cpu}
+                'roofline': roofline, 'roofline_secondary': secondary, 'parity_vs_oracle': parity, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

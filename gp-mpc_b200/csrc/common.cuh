@@ -60,14 +60,22 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// bounded wait: a protocol error traps instead of hanging the GPU
+// bounded wait: a protocol error traps instead of hanging the GPU.  The bound is wall time
+// (%globaltimer, ~20 s), not a spin count, so debuggers / compute-sanitizer / MPS time slicing
+// cannot trip it.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok = 0, spins = 0;
+    uint64_t t0 = 0;
     do {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 24)) __trap();
+        if (!ok && (++spins & 0xfffu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
     } while (!ok);
 }
 // global -> shared bulk copy of `bytes` (multiple of 16), completion counted on `bar`

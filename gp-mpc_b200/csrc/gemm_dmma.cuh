@@ -12,6 +12,7 @@
 // All dimensions are multiples of the tile sizes (every matrix in the engine is padded
 // to GPMPC_TILE with an identity tail), so there is no bounds handling anywhere.
 #pragma once
+#include <atomic>
 #include "common.cuh"
 
 enum : int {
@@ -224,13 +225,13 @@ static cudaError_t gemm_launch(const GemmParams& p, int batch, int nchunks, cuda
     using SM = GemmSmem<BM, BN, BT, STAGES>;
     auto kern = gemm_dmma_kernel<BM, BN, WM, WN, BT, STAGES, MINB, TMA>;
     constexpr int BYTES = SM::BYTES + (TMA ? STAGES * 8 : 0);
-    static bool configured[GPMPC_MAX_DEVICES] = {false};       // the attribute is per device
+    static std::atomic<bool> configured[GPMPC_MAX_DEVICES];    // the attribute is per device; set-attribute is idempotent
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < GPMPC_MAX_DEVICES && !configured[dev]) {
+    if (dev >= 0 && dev < GPMPC_MAX_DEVICES && !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        configured[dev].store(true, std::memory_order_release);
     }
     constexpr int R = (BM >= BN) ? BM / BN : 1;
     const int tiles = p.lower ? R * p.mt * (p.mt + 1) / 2 : p.mt * p.nt;
@@ -432,13 +433,13 @@ static cudaError_t gemm_tmap_launch(const GemmParams& p, int batch, int nchunks,
 {
     auto kern = gemm_dmma_tmap_kernel<BM, BN, WM, WN, STAGES, MINB>;
     constexpr int BYTES = STAGES * (BM + BN) * GEMM_BK * 8 + STAGES * 8 + 1024;
-    static bool configured[GPMPC_MAX_DEVICES] = {false};       // the attribute is per device
+    static std::atomic<bool> configured[GPMPC_MAX_DEVICES];    // the attribute is per device; set-attribute is idempotent
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < GPMPC_MAX_DEVICES && !configured[dev]) {
+    if (dev >= 0 && dev < GPMPC_MAX_DEVICES && !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        configured[dev].store(true, std::memory_order_release);
     }
     CUtensorMap tmA, tmB;
     if (!tmap_make(&tmA, p.A, p.K, p.mt * BM, p.lda, p.sA, batch, BM)) return cudaErrorInvalidValue;

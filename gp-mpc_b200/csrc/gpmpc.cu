@@ -9,16 +9,20 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
 #include "gemm_dmma.cuh"
+#include "predict_streamk.cuh"
 #include "kernels.cuh"
 
 #define GPMPC_VERSION 100
 #define HB 64                 // test points per predict pass (rows of the KS^T operand)
-#define MAX_CHUNKS 32         // split-K partial slots per output
 #define NX_MAX 32
+#define PSK_MAX_CTAS 1024
 #define MAX_DEPTH 12           // recursion depth bound: 128 * 2^12 rows
 
 // ------------------------------------------------------------------------------------
@@ -74,7 +78,10 @@ struct gpmpc_handle_s {
     double *dAlpha = nullptr, *dTmp = nullptr, *dRes = nullptr;
     int* dInfo = nullptr;
     // predict
-    double *dKST = nullptr, *dPart = nullptr, *dPMJ = nullptr, *dSQ = nullptr, *dV = nullptr, *dR = nullptr;
+    double *dKST = nullptr, *dPart = nullptr, *dPMJ = nullptr, *dSQ = nullptr, *dV = nullptr, *dR = nullptr, *dR2 = nullptr;
+    unsigned int* dCnt = nullptr;     // stream-K counters: [nloc*nt tile | nloc output | 1 done], self-cleaning
+    int psk_ctas = 0, opt_predict_ctas = 0;   // persistent grid of the predict product (2 CTAs per SM)
+    double *dCovV = nullptr, *dCovOut = nullptr; long long covVcap = 0, covOutcap = 0;   // GP.covar scratch pool
     double *dG = nullptr, *dZ = nullptr, *dSigma = nullptr, *dMean = nullptr, *dVar = nullptr, *dJ = nullptr, *dCov = nullptr;
     double *dIn = nullptr, *dOut = nullptr;   // [Z | Sigma] and [mean | var | J | cov] slabs: one H2D + one D2H per host call
     int Hcap = 0;
@@ -89,14 +96,14 @@ struct gpmpc_handle_s {
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_ksplit = 0, opt_gemm_variant = 3, opt_tri_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 592;   // 128x64-tile count below which 64x32 tiles are used
+    int opt_refine = 0, opt_gemm_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 592;   // 128x64-tile count below which 64x32 tiles are used
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     // peer (CUDA IPC) exchange: [flags: 2*MAXW u64][gather buffer parity 0][parity 1]
     double* dPeerBlock = nullptr; long long peerGsz = 0; int peerHcap = 0; bool peer_ready = false;
     double* peerBase[GPMPC_MAXW] = {nullptr}; bool peerOpened[GPMPC_MAXW] = {false};
-    unsigned int* dPeerCounter = nullptr; int* dPeerStatus = nullptr; int* hPeerStatus = nullptr;
-    unsigned long long peer_step = 0; int opt_peer = 1;
+    int* dPeerStatus = nullptr; int* hPeerStatus = nullptr;
+    unsigned long long peer_step = 0; int opt_peer = 1; double opt_peer_timeout_s = 60.0; int clock_khz = 1965000;
     char err[512] = "";
 };
 
@@ -106,6 +113,12 @@ static void set_error(gpmpc_handle_t h, const char* fmt, ...)
     vsnprintf(h ? h->err : g_create_err, 512, fmt, ap);
     va_end(ap);
 }
+
+// NVTX range per phase (header-only nvtx3: a no-op unless a profiler injects the library)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static inline long long slab(gpmpc_handle_t h) { return (long long)h->Npad * h->Npad; }
 static inline long long wslab(gpmpc_handle_t h) { return (long long)h->Npad * h->Npad / 4 + 128; }
@@ -170,11 +183,11 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
 {
     const int ld = h->Npad;
     if (n <= LEAF_N) {
-        static bool conf[GPMPC_MAX_DEVICES] = {false};
-        if (!conf[h->device % GPMPC_MAX_DEVICES]) {
+        static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
+        if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
             CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_N * LEAF_LD * 8));
             CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_DOUBLES * 8));
-            conf[h->device % GPMPC_MAX_DEVICES] = true;
+            conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
         }
         if (h->opt_leaf_variant == 0)
             leaf_potrf_trtri_kernel<<<batch, 256, LEAF_N * LEAF_LD * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
@@ -255,13 +268,13 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
 // output slabs at K (stride slab).  full = 1 writes the whole square, 0 the lower triangle.
 static int launch_kbuild(gpmpc_handle_t h, const double* dHyp, const double* dJit, double* K, int batch, int full)
 {
-    static bool conf[GPMPC_MAX_DEVICES] = {false};
+    static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
     const int KD = (h->Nx + 3) & ~3, S = ((KD >> 2) & 1) ? KD : KD + 4;
     const int smem = (2 * KB2_TILE * S + 2 * KB2_TILE + 16) * 8;
-    if (!conf[h->device % GPMPC_MAX_DEVICES]) {
+    if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
         CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * KB2_TILE * 36 + 2 * KB2_TILE + 16) * 8));
-        conf[h->device % GPMPC_MAX_DEVICES] = true;
+        conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
     }
     const int T = h->Npad / KB2_TILE;
     dim3 grid(T * (T + 1) / 2, 1, batch);
@@ -333,30 +346,10 @@ extern "C" const char* gpmpc_last_error(gpmpc_handle_t h) { return h ? h->err : 
         cudaMemsetAsync((ptr), 0, (size_t)(count) * sizeof(*(ptr)), h->st);             \
     } while (0)
 
-extern "C" int gpmpc_create(int N, int Nx, int Ny, int out_begin, int out_count, int device, gpmpc_handle_t* out)
+extern "C" int gpmpc_destroy(gpmpc_handle_t h);
+
+static int create_fill(gpmpc_handle_t h, int N, int Nx, int Ny, int out_begin, int out_count, int device)
 {
-    gpmpc_handle_t h = nullptr;
-    if (!out) return GPMPC_ERR_ARG;
-    *out = nullptr;
-    if (N < 1 || Nx < 1 || Nx > NX_MAX || Ny < 1 || out_begin < 0 || out_count < 1 || out_begin + out_count > Ny) {
-        set_error(nullptr, "gpmpc_create: bad sizes N=%d Nx=%d (max %d) Ny=%d outputs [%d,%d)", N, Nx, NX_MAX, Ny,
-                  out_begin, out_begin + out_count);
-        return GPMPC_ERR_ARG;
-    }
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) {
-        set_error(nullptr, "gpmpc_create: no usable CUDA device %d (count %d, %s) -- this engine has no CPU path",
-                  device, ndev, cudaGetErrorString(e));
-        return GPMPC_ERR_CUDA;
-    }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
-        set_error(nullptr, "gpmpc_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
-                  prop.major, prop.minor);
-        return GPMPC_ERR_CUDA;
-    }
-    h = new gpmpc_handle_s();
     h->N = N; h->Nx = Nx; h->Ny = Ny; h->a0 = out_begin; h->nloc = out_count; h->device = device;
     h->nloc_max = out_count; h->world = 1; h->rank = 0;
     h->Npad = (N + GPMPC_TILE - 1) / GPMPC_TILE * GPMPC_TILE;
@@ -404,6 +397,40 @@ extern "C" int gpmpc_create(int N, int Nx, int Ny, int out_begin, int out_count,
     h->hyper.assign((size_t)out_count * (Nx + 2), 0.0);
     h->logdet.assign(out_count, 0.0); h->yalpha.assign(out_count, 0.0); h->jitter_used.assign(out_count, 0);
     CUDA_TRY(cudaStreamSynchronize(h->st));
+    return GPMPC_OK;
+}
+
+
+extern "C" int gpmpc_create(int N, int Nx, int Ny, int out_begin, int out_count, int device, gpmpc_handle_t* out)
+{
+    gpmpc_handle_t h = nullptr;
+    if (!out) return GPMPC_ERR_ARG;
+    *out = nullptr;
+    if (N < 1 || Nx < 1 || Nx > NX_MAX || Ny < 1 || out_begin < 0 || out_count < 1 || out_begin + out_count > Ny) {
+        set_error(nullptr, "gpmpc_create: bad sizes N=%d Nx=%d (max %d) Ny=%d outputs [%d,%d)", N, Nx, NX_MAX, Ny,
+                  out_begin, out_begin + out_count);
+        return GPMPC_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) {
+        set_error(nullptr, "gpmpc_create: no usable CUDA device %d (count %d, %s) -- this engine has no CPU path",
+                  device, ndev, cudaGetErrorString(e));
+        return GPMPC_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        set_error(nullptr, "gpmpc_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                  prop.major, prop.minor);
+        return GPMPC_ERR_CUDA;
+    }
+    h = new gpmpc_handle_s();
+    const int rc = create_fill(h, N, Nx, Ny, out_begin, out_count, device);
+    if (rc != GPMPC_OK) {            // no partially built handle survives: message to the create slot, everything freed
+        snprintf(g_create_err, sizeof(g_create_err), "gpmpc_create: %s", h->err);
+        gpmpc_destroy(h);
+        return rc;
+    }
     *out = h;
     return GPMPC_OK;
 }
@@ -416,10 +443,10 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int r = 0; r < GPMPC_MAXW; ++r) if (h->peerOpened[r]) cudaIpcCloseMemHandle(h->peerBase[r]);
     if (h->dPeerBlock) cudaFree(h->dPeerBlock);
-    if (h->dPeerCounter) cudaFree(h->dPeerCounter);
+    if (h->dCnt) cudaFree(h->dCnt);
     if (h->hPeerStatus) cudaFreeHost(h->hPeerStatus);
     double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
-                      h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dG, h->dIn, h->dOut, h->dU, h->dKinv, h->dGradPart, h->dGrad,
+                      h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dR2, h->dCovV, h->dCovOut, h->dG, h->dIn, h->dOut, h->dU, h->dKinv, h->dGradPart, h->dGrad,
                       h->dKinvAll, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
@@ -665,13 +692,13 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
 {
     if (!h || !name) return GPMPC_ERR_ARG;
     if (!strcmp(name, "refine")) { h->opt_refine = value != 0.0; return GPMPC_OK; }
-    if (!strcmp(name, "ksplit")) {
+    if (!strcmp(name, "predict_ctas")) {       // persistent grid of the predict product (0 = 2 per SM)
         const int v = (int)value;
-        if (v < 0 || v % 128) { set_error(h, "ksplit must be a non-negative multiple of 128"); return GPMPC_ERR_ARG; }
-        h->opt_ksplit = v; return GPMPC_OK;
+        if (v < 0 || v > PSK_MAX_CTAS) { set_error(h, "predict_ctas must be in [0, %d]", PSK_MAX_CTAS); return GPMPC_ERR_ARG; }
+        h->opt_predict_ctas = v; return GPMPC_OK;
     }
+    if (!strcmp(name, "peer_timeout_s")) { h->opt_peer_timeout_s = value > 0.0 ? value : 60.0; return GPMPC_OK; }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
-    if (!strcmp(name, "tri_variant")) { h->opt_tri_variant = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "small_tiles")) { h->opt_small_tiles = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "peer")) { h->opt_peer = value != 0.0; return GPMPC_OK; }
@@ -687,14 +714,20 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
 {
     const long long np = h->Npad;
     if (!h->dKST) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, h->device);
+        h->psk_ctas = 2 * sms;
+        const long long nt = np / 128;
         ALLOC(h->dKST, (long long)h->nloc * HB * np);
-        ALLOC(h->dPart, (long long)h->nloc * MAX_CHUNKS * HB * np);
+        ALLOC(h->dPart, (long long)PSK_MAX_CTAS * 2 * HB * PSK_BN);
         ALLOC(h->dPMJ, (long long)h->nloc * HB * ((np + 1023) / 1024) * (h->Nx + 1));
-        ALLOC(h->dSQ, (long long)h->nloc * HB * ((np + 255) / 256));
+        ALLOC(h->dSQ, (long long)h->nloc * HB * nt);
+        ALLOC(h->dCnt, (long long)h->nloc * nt + h->nloc + 1);
     }
-    if (h->opt_refine && !h->dV) {
-        ALLOC(h->dV, (long long)h->nloc * HB * np);
-        ALLOC(h->dR, (long long)h->nloc * HB * np);
+    if (h->opt_refine && !h->dR2) {
+        if (!h->dV) { ALLOC(h->dV, (long long)h->nloc * HB * np); ALLOC(h->dR, (long long)h->nloc * HB * np); }
+        ALLOC(h->dR2, (long long)h->nloc * HB * np);
     }
     if (H > h->Hcap) {
         CUDA_TRY(cudaStreamSynchronize(h->st));
@@ -715,67 +748,62 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
     return GPMPC_OK;
 }
 
-// Split-K chunk of the predict product.  Work item (j-tile, chunk) costs its k-tiles plus a fixed
-// prologue/epilogue; items are dispatched longest-first onto 2 CTA slots per SM.  The chunk is
-// picked by simulating that list schedule for a few candidates (cheap: <= a few thousand items)
-// -- more chunks balance the triangular workload, fewer chunks save per-item overhead and
-// partial-sum traffic.
-static int choose_ksplit(gpmpc_handle_t h)
-{
-    const int np = h->Npad, nt = np / 128;
-    if (h->opt_ksplit) return h->opt_ksplit >= np ? 0 : std::max(h->opt_ksplit, (np / MAX_CHUNKS + 127) / 128 * 128);
-    static int cache_np = -1, cache_nl = -1, cache_ks = 0;
-    if (cache_np == np && cache_nl == h->nloc) return cache_ks;
-    const int cands[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 1 << 20};
-    const int slots = 296;
-    const double overhead = 0.5;           // k-tile equivalents per item (pipeline fill, partial store, reduce)
-    const int cap = std::max(2, nt / 8);   // measured: chunks longer than N/8 lose to the tail (two CTAs share an SM)
-    double best = 1e300; int best_tiles = 1 << 20;
-    std::vector<double> slot(slots);
-    for (int ct : cands) {
-        if (ct < nt && ct > cap && nt > 16) continue;
-        const int nch = (ct >= nt) ? 1 : (nt + ct - 1) / ct;
-        if (nch > MAX_CHUNKS) continue;
-        std::fill(slot.begin(), slot.end(), 0.0);
-        // dispatch order of the kernel: chunk-major, j-tile descending, outputs innermost
-        for (int c = 0; c < nch; ++c)
-            for (int jt = nt - 1; jt >= 0; --jt) {
-                const int lo = (ct >= nt) ? 0 : c * ct, hi = std::min(jt + 1, (ct >= nt) ? nt : (c + 1) * ct);
-                if (hi <= lo) continue;
-                for (int a = 0; a < h->nloc; ++a) {
-                    auto it = std::min_element(slot.begin(), slot.end());
-                    *it += (hi - lo) + overhead;
-                }
-            }
-        const double mk = *std::max_element(slot.begin(), slot.end());
-        if (mk < best - 1e-9) { best = mk; best_tiles = ct; }
-    }
-    cache_np = np; cache_nl = h->nloc;
-    cache_ks = (best_tiles >= nt) ? 0 : best_tiles * 128;
-    return cache_ks;
-}
-
+// Persistent stream-K launch of the fused predict product (predict_streamk.cuh)
 template <int BM>
-static cudaError_t trigemm_bm(int variant, const GemmParams& p, int batch, int nch, cudaStream_t st)
+static cudaError_t psk_launch_bm(const PredictParams& p, const double* A, long long sA, const double* B, long long sB,
+                                 int np, int grid, cudaStream_t st)
 {
-    if (variant == 3) return gemm_tmap_launch<BM, 128, 1, 8, 4, 2>(p, batch, nch, st);          // tensor-map TMA feed
-    if (variant == 2) return gemm_launch<BM, 128, 1, 8, true, 3, 2, true>(p, batch, nch, st);   // TMA feed
-    if (variant == 1) return gemm_launch<BM, 128, 1, 8, true, 3, 2>(p, batch, nch, st);   // 2 CTAs/SM
-    return gemm_launch<BM, 128, 1, 8, true, 4, 1>(p, batch, nch, st);
+    auto kern = predict_streamk_kernel<BM>;
+    constexpr int BYTES = PSK_STAGES * (BM + PSK_BN) * GEMM_BK * 8 + PSK_STAGES * 8 + 1024;
+    static std::atomic<bool> configured[GPMPC_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < GPMPC_MAX_DEVICES && !configured[dev].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
+        if (e != cudaSuccess) return e;
+        configured[dev].store(true, std::memory_order_release);
+    }
+    CUtensorMap tmA, tmB;
+    if (!tmap_make(&tmA, A, np, BM, np, sA, p.nloc, BM)) return cudaErrorInvalidValue;
+    if (!tmap_make(&tmB, B, np, np, np, sB, p.nloc, PSK_BN)) return cudaErrorInvalidValue;
+    kern<<<grid, PSK_THREADS, BYTES, st>>>(p, tmA, tmB);
+    return cudaGetLastError();
 }
 
-static cudaError_t trigemm_launch(int variant, int bm, const GemmParams& p, int batch, int nch, cudaStream_t st)
+static cudaError_t psk_launch(int bm, const PredictParams& p, const double* A, long long sA, const double* B, long long sB,
+                              int np, int grid, cudaStream_t st)
 {
     switch (bm) {
-    case 8: return trigemm_bm<8>(variant, p, batch, nch, st);
-    case 16: return trigemm_bm<16>(variant, p, batch, nch, st);
-    case 24: return trigemm_bm<24>(variant, p, batch, nch, st);
-    case 32: return trigemm_bm<32>(variant, p, batch, nch, st);
-    case 40: return trigemm_bm<40>(variant, p, batch, nch, st);
-    case 48: return trigemm_bm<48>(variant, p, batch, nch, st);
-    case 56: return trigemm_bm<56>(variant, p, batch, nch, st);
-    default: return trigemm_bm<64>(variant, p, batch, nch, st);
+    case 8: return psk_launch_bm<8>(p, A, sA, B, sB, np, grid, st);
+    case 16: return psk_launch_bm<16>(p, A, sA, B, sB, np, grid, st);
+    case 24: return psk_launch_bm<24>(p, A, sA, B, sB, np, grid, st);
+    case 32: return psk_launch_bm<32>(p, A, sA, B, sB, np, grid, st);
+    case 40: return psk_launch_bm<40>(p, A, sA, B, sB, np, grid, st);
+    case 48: return psk_launch_bm<48>(p, A, sA, B, sB, np, grid, st);
+    case 56: return psk_launch_bm<56>(p, A, sA, B, sB, np, grid, st);
+    default: return psk_launch_bm<64>(p, A, sA, B, sB, np, grid, st);
     }
+}
+
+// persistent grid: 2 CTAs per SM, but never fewer than 32 k-steps per CTA
+static int psk_grid(gpmpc_handle_t h, long long G)
+{
+    int ctas = h->opt_predict_ctas > 0 ? h->opt_predict_ctas : h->psk_ctas;
+    ctas = std::min(ctas, PSK_MAX_CTAS);
+    const long long by_work = std::max(1LL, G / 32);
+    return (int)std::min<long long>(ctas, h->opt_predict_ctas > 0 ? G : by_work);
+}
+
+static void psk_base(gpmpc_handle_t h, PredictParams& p, int Hc)
+{
+    memset(&p, 0, sizeof(p));
+    const long long nt = h->Npad / 128;
+    p.nloc = h->nloc; p.nt = (int)nt; p.Hc = Hc;
+    p.T = 4 * nt * (nt + 1); p.G = p.T * h->nloc;
+    p.part = h->dPart;
+    p.tile_cnt = h->dCnt; p.out_cnt = h->dCnt + (long long)h->nloc * nt; p.done_cnt = p.out_cnt + h->nloc;
+    p.SQ = h->dSQ;
+    p.hyp = h->dHyp; p.hyp_ld = h->Nx + 2; p.Nx = h->Nx;
 }
 
 static inline int ks_chunk(gpmpc_handle_t h) { return h->Npad <= 4096 ? 1024 : KS_CHUNK; }
@@ -804,26 +832,15 @@ static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, in
     return launch_ks<32>(h, dZc, Hc, bm, nblk);
 }
 
-// C = alpha * A(h-major rows) * T^T (+ Cin) with T = Li or L (lower), reduced over split-K
-// into `Vout` (may be null) and squared-norm partials into dSQ when sq != 0
-static int tri_product(gpmpc_handle_t h, const double* Amat, const double* T, int bm, int Hc, int ksplit,
-                       double* Vout)
+// rows of Amat (h-major, stride HB*np per output) times T^T with T = Li or L (lower triangular):
+// the solved rows go to Vout (may be null), their per-tile squared norms to dSQ
+static int tri_product(gpmpc_handle_t h, const double* Amat, const double* T, int bm, int Hc, double* Vout)
 {
     const int np = h->Npad;
-    const int nch = ksplit ? (np + ksplit - 1) / ksplit : 1;
-    GemmParams p;
-    memset(&p, 0, sizeof(p));
-    p.A = Amat; p.lda = np; p.sA = (long long)HB * np;
-    p.B = T; p.ldb = np; p.sB = slab(h);
-    p.C = h->dPart; p.ldc = np; p.sC = (long long)MAX_CHUNKS * HB * np;
-    p.mt = 1; p.nt = np / 128; p.K = np; p.alpha = 1.0; p.beta = 0.0; p.kflags = GEMM_KJ_LE;
-    p.ksplit = ksplit; p.sPart = (long long)HB * np; p.lpt = 1;
-    CUDA_TRY(trigemm_launch(h->opt_tri_variant, bm, p, h->nloc, nch, h->st));
-    const int nblk_sq = (np + 255) / 256;
-    dim3 g(nblk_sq, Hc, h->nloc);
-    reduce_sq_kernel<<<g, 256, 0, h->st>>>(h->dPart, np, (long long)HB * np, (long long)MAX_CHUNKS * HB * np, ksplit, np, Hc,
-                                            h->dSQ, nblk_sq, Vout, (long long)HB * np);
-    CUDA_TRY(cudaGetLastError());
+    PredictParams p;
+    psk_base(h, p, Hc);
+    p.Vout = Vout; p.sV = (long long)HB * np; p.ldv = np;
+    CUDA_TRY(psk_launch(bm, p, Amat, (long long)HB * np, T, slab(h), np, psk_grid(h, p.G), h->st));
     return GPMPC_OK;
 }
 
@@ -842,10 +859,12 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
                         double* d_mean, double* d_var, double* d_cov, double* d_jac)
 {
     const int np = h->Npad, Nx = h->Nx;
-    const int ksplit = choose_ksplit(h);
-    const int nblk_mj = (np + ks_chunk(h) - 1) / ks_chunk(h), nblk_sq = (np + 255) / 256;
+    const int nblk_mj = (np + ks_chunk(h) - 1) / ks_chunk(h);
+    NvtxRange nvtx_r("gpmpc.predict");
     // fused epilogue + all-gather over peer memory when the exchange block is attached
     const int use_peers = (h->world > 1 && h->peer_ready && h->opt_peer && H <= h->peerHcap) ? 1 : 0;
+    const int nccl_gather = (h->world > 1 && !use_peers) ? 1 : 0;
+    const long long timeout_clocks = (long long)(h->opt_peer_timeout_s * 1e3 * (double)h->clock_khz);
     PeerArgs pa;
     memset(&pa, 0, sizeof(pa));
     if (use_peers) {
@@ -855,55 +874,62 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
         pa.goff = 2 * GPMPC_MAXW + (long long)(h->peer_step & 1) * h->peerGsz;
         pa.flag_idx = (int)(h->peer_step & 1) * GPMPC_MAXW + h->rank;
         pa.step = h->peer_step;
-        pa.counter = h->dPeerCounter;
-        pa.total_blocks = (unsigned int)H * h->nloc;
-        CUDA_TRY(cudaMemsetAsync(h->dPeerCounter, 0, sizeof(unsigned int), h->st));
+        pa.timeout_clocks = timeout_clocks;
     }
+    AssembleArgs as;
+    memset(&as, 0, sizeof(as));
+    as.G = use_peers ? h->dPeerBlock + pa.goff : h->dG;
+    as.Ny = h->Ny; as.Nx = Nx; as.H = H; as.method_ta = (method == GPMPC_METHOD_TA);
+    as.Sigma = dSigma; as.sigma_per_point = spp;
+    as.mean = d_mean; as.var = d_var; as.J = d_jac; as.cov = d_cov;
+    as.flags = use_peers ? reinterpret_cast<const unsigned long long*>(h->dPeerBlock) + (h->peer_step & 1) * GPMPC_MAXW : nullptr;
+    as.world = h->world; as.step = h->peer_step; as.status = h->dPeerStatus; as.timeout_clocks = timeout_clocks;
+    // one chunk and no NCCL call in between: the product kernel's last CTA assembles too (2 launches per step)
+    const bool fused_assemble = (H <= HB) && !nccl_gather;
     for (int h0 = 0; h0 < H; h0 += HB) {
         const int Hc = std::min(HB, H - h0);
         const int bm = (Hc + 7) / 8 * 8;
+        const bool last_chunk = (h0 + HB >= H);
         const double* dZc = dZ + (long long)h0 * Nx;
         CUDA_TRY(launch_ks_any(h, dZc, Hc, bm, nblk_mj));
+        PredictParams p;
+        psk_base(h, p, Hc);
+        p.finalize = 1;
+        p.PMJ = h->dPMJ; p.nblk_mj = nblk_mj;
+        p.Gloc = h->dG; p.slot0 = h->a0; p.Htot = H; p.h0 = h0;
+        p.pa = pa; p.use_peers = use_peers; p.publish = last_chunk ? 1 : 0;
+        p.as = as; p.do_assemble = (fused_assemble && !h->opt_refine) ? 1 : 0;
         if (!h->opt_refine) {
-            int rc = tri_product(h, h->dKST, h->dLi, bm, Hc, ksplit, nullptr);
-            if (rc) return rc;
+            CUDA_TRY(psk_launch(bm, p, h->dKST, (long long)HB * np, h->dLi, slab(h), np, psk_grid(h, p.G), h->st));
         } else {
             // v1 = Li ks ; r = ks - L v1 ; v = v1 + Li r   (one step of iterative refinement)
-            int rc = tri_product(h, h->dKST, h->dLi, bm, Hc, ksplit, h->dV);
+            int rc = tri_product(h, h->dKST, h->dLi, bm, Hc, h->dV);
             if (rc) return rc;
-            rc = tri_product(h, h->dV, h->dL, bm, Hc, ksplit, h->dR);          // dR = L v1
+            rc = tri_product(h, h->dV, h->dL, bm, Hc, h->dR);                  // dR = L v1
             if (rc) return rc;
             dim3 g((np + 255) / 256, bm, h->nloc);
             axpby_rows_kernel<<<g, 256, 0, h->st>>>(h->dKST, h->dR, 1.0, -1.0, h->dR, np, (long long)HB * np, bm);
             CUDA_TRY(cudaGetLastError());
-            rc = tri_product(h, h->dR, h->dLi, bm, Hc, ksplit, h->dR);         // dR = Li r
+            rc = tri_product(h, h->dR, h->dLi, bm, Hc, h->dR2);                // dR2 = Li r
             if (rc) return rc;
-            axpby_rows_kernel<<<g, 256, 0, h->st>>>(h->dV, h->dR, 1.0, 1.0, h->dV, np, (long long)HB * np, bm);
+            axpby_rows_kernel<<<g, 256, 0, h->st>>>(h->dV, h->dR2, 1.0, 1.0, h->dV, np, (long long)HB * np, bm);
             CUDA_TRY(cudaGetLastError());
-            // squared norms of the refined v: reuse the reducer with a single "chunk" = dV itself
-            dim3 g2(nblk_sq, Hc, h->nloc);
-            reduce_sq_kernel<<<g2, 256, 0, h->st>>>(h->dV, np, 0, (long long)HB * np, 0, np, Hc, h->dSQ, nblk_sq, nullptr, 0);
+            sq_rows_kernel<<<dim3(np / 128, Hc, h->nloc), 128, 0, h->st>>>(h->dV, np, (long long)HB * np, h->dSQ, np / 128);
+            CUDA_TRY(cudaGetLastError());
+            finalize_kernel<<<h->nloc, PSK_THREADS, 0, h->st>>>(p);
             CUDA_TRY(cudaGetLastError());
         }
-        dim3 gf(Hc, h->nloc);
-        finalize_local_kernel<<<gf, 64, 0, h->st>>>(h->dPMJ, nblk_mj, h->dSQ, nblk_sq, h->dHyp, Nx + 2, Nx, Hc,
-                                                     h->dG, h->a0, H, h0, pa, use_peers);
-        CUDA_TRY(cudaGetLastError());
     }
-    const double* Gsrc = h->dG;
-    const unsigned long long* flags = nullptr;
-    if (use_peers) {
-        Gsrc = h->dPeerBlock + pa.goff;
-        flags = reinterpret_cast<const unsigned long long*>(h->dPeerBlock) + (h->peer_step & 1) * GPMPC_MAXW;
-    } else if (h->world > 1) {
+    if (nccl_gather) {
         const size_t cnt = (size_t)h->nloc_max * H * (Nx + 2);
         int r = g_nccl.AllGather(h->dG + (size_t)h->rank * cnt, h->dG, cnt, 8 /* ncclFloat64 */, h->comm, h->st);
         if (r) { set_error(h, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return GPMPC_ERR_NCCL; }
     }
-    const int smem = (2 * h->Ny * Nx + h->Ny) * 8;
-    assemble_kernel<<<H, 128, smem, h->st>>>(Gsrc, h->Ny, Nx, H, method == GPMPC_METHOD_TA, dSigma, spp,
-                                              d_mean, d_var, d_jac, d_cov, flags, h->world, h->peer_step, h->dPeerStatus);
-    CUDA_TRY(cudaGetLastError());
+    if (!fused_assemble || h->opt_refine) {
+        const int smem = (2 * h->Ny * Nx + h->Ny) * 8;
+        assemble_kernel<<<std::min(H, 2048), 128, smem, h->st>>>(as);
+        CUDA_TRY(cudaGetLastError());
+    }
     return GPMPC_OK;
 }
 
@@ -1190,19 +1216,31 @@ extern "C" int gpmpc_posterior_cov(gpmpc_handle_t h, int H, const double* Z, dou
     if (rc) return rc;
     const int np = h->Npad, Nx = h->Nx, nl = h->nloc;
     const long long sVall = (long long)H * np;            // all H solved rows of one output
-    double *dVall = nullptr, *dOut = nullptr;
-    ALLOC(dVall, (long long)nl * sVall);
-    ALLOC(dOut, (long long)nl * H * H);
+    // scratch is pooled on the handle (grown on demand), not allocated per call
+    if ((long long)nl * sVall > h->covVcap) {
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (h->dCovV) cudaFree(h->dCovV);
+        h->dCovV = nullptr; h->covVcap = 0;
+        ALLOC(h->dCovV, (long long)nl * sVall);
+        h->covVcap = (long long)nl * sVall;
+    }
+    if ((long long)nl * H * H > h->covOutcap) {
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (h->dCovOut) cudaFree(h->dCovOut);
+        h->dCovOut = nullptr; h->covOutcap = 0;
+        ALLOC(h->dCovOut, (long long)nl * H * H);
+        h->covOutcap = (long long)nl * H * H;
+    }
+    double *dVall = h->dCovV, *dOut = h->dCovOut;
     if (!h->dV) { ALLOC(h->dV, (long long)nl * HB * np); ALLOC(h->dR, (long long)nl * HB * np); }
     CUDA_TRY(cudaMemcpyAsync(h->dZ, Z, (size_t)H * Nx * 8, cudaMemcpyHostToDevice, h->st));
-    const int ksplit = choose_ksplit(h);
     const int nblk_mj = (np + ks_chunk(h) - 1) / ks_chunk(h);
     for (int h0 = 0; h0 < H && rc == GPMPC_OK; h0 += HB) {
         const int Hc = std::min(HB, H - h0), bm = (Hc + 7) / 8 * 8;
         const double* dZc = h->dZ + (long long)h0 * Nx;
         cudaError_t e = launch_ks_any(h, dZc, Hc, bm, nblk_mj);
         if (e != cudaSuccess) { set_error(h, "posterior_cov ks: %s", cudaGetErrorString(e)); rc = GPMPC_ERR_CUDA; break; }
-        rc = tri_product(h, h->dKST, h->dLi, bm, Hc, ksplit, h->dV);
+        rc = tri_product(h, h->dKST, h->dLi, bm, Hc, h->dV);
         if (rc) break;
         dim3 g(1, Hc, nl);
         copy2d_kernel<<<dim3(16, std::min(Hc, 64), nl), 128, 0, h->st>>>(h->dV, np, (long long)HB * np,
@@ -1215,7 +1253,6 @@ extern "C" int gpmpc_posterior_cov(gpmpc_handle_t h, int H, const double* Z, dou
     }
     if (rc == GPMPC_OK && cudaMemcpyAsync(out, dOut, (size_t)nl * H * H * 8, cudaMemcpyDeviceToHost, h->st) != cudaSuccess) rc = GPMPC_ERR_CUDA;
     cudaStreamSynchronize(h->st);
-    cudaFree(dVall); cudaFree(dOut);
     if (rc == GPMPC_ERR_CUDA) set_error(h, "gpmpc_posterior_cov: CUDA failure %s", cudaGetErrorString(cudaGetLastError()));
     return rc;
 }
@@ -1266,7 +1303,6 @@ extern "C" int gpmpc_peer_export(gpmpc_handle_t h, int Hcap, void* handle64)
     h->peerGsz = (long long)nyp * Hcap * (h->Nx + 2);
     h->peerHcap = Hcap;
     ALLOC(h->dPeerBlock, 2 * GPMPC_MAXW + 2 * h->peerGsz);
-    ALLOC(h->dPeerCounter, 1);
     if (!h->dPeerStatus) {     // status word in mapped pinned host memory: the host reads it without a copy
         CUDA_TRY(cudaHostAlloc((void**)&h->hPeerStatus, sizeof(int), cudaHostAllocMapped));
         *h->hPeerStatus = 0;
@@ -1343,7 +1379,7 @@ extern "C" int gpmpc_profile(gpmpc_handle_t h, int what, int n, int reps, double
         }
         case GPMPC_PROF_TRIGEMM: {
             const int Hc = (n > 0 && n <= HB) ? n : 56;
-            return tri_product(h, h->dKST, h->dLi, (Hc + 7) / 8 * 8, Hc, choose_ksplit(h), nullptr);
+            return tri_product(h, h->dKST, h->dLi, (Hc + 7) / 8 * 8, Hc, nullptr);
         }
         default: set_error(h, "gpmpc_profile: unknown selector %d", what); return GPMPC_ERR_ARG;
         }

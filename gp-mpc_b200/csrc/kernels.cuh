@@ -587,158 +587,6 @@ ks_mean_jac_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
     }
 }
 
-// stage 3: v_i = sum over valid split-K chunks; partial column norms  sum_i v_i^2
-//   (var = sf2 - v^T v, gp_functions.py:125-126,136).  grid (Npad/256, H, outputs)
-__global__ void __launch_bounds__(256)
-reduce_sq_kernel(const double* __restrict__ Part, int ldp, long long sPart, long long sPa,
-                 int ksplit, int Kdim, int H, double* __restrict__ SQ, int nblk,
-                 double* __restrict__ Vout, long long sV)
-{
-    __shared__ double red[8];
-    const int a = blockIdx.z, h = blockIdx.y;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    int nch = 1;
-    if (ksplit) {
-        const int khi = min(Kdim, ((i >> 7) + 1) * 128);
-        nch = (khi + ksplit - 1) / ksplit;
-    }
-    const double* p = Part + (long long)a * sPa + (long long)h * ldp + i;
-    double v = 0.0;
-    if (i < Kdim) {
-        for (int c = 0; c < nch; ++c) v += p[(long long)c * sPart];
-        if (Vout) Vout[(long long)a * sV + (long long)h * ldp + i] = v;
-    }
-    double s = warp_sum(v * v);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double r = 0.0;
-        for (int q = 0; q < 8; ++q) r += red[q];
-        SQ[((long long)a * H + h) * nblk + blockIdx.x] = r;
-    }
-}
-
-// stage 4: per local output and test point: [mean, var, J_0..J_{Nx-1}] into the gather
-// buffer G[slot][h][2+Nx]  (slot = global output index; one contiguous chunk per rank)
-#define GPMPC_MAXW 16
-// Peer ("fused epilogue + all-gather") mode: instead of writing into the local gather buffer and
-// calling ncclAllGather, every rank stores its [mean,var,J] records directly into the gather
-// buffer of EVERY rank (peer pointers mapped with CUDA IPC, NVLink/NVSwitch P2P stores), then the
-// last block to finish publishes a per-source flag on every peer (release at system scope).
-// The consumer (assemble_kernel) acquires all `world` flags before reading.  Buffers are
-// double-buffered by step parity; in-order streams make that sufficient.
-struct PeerArgs {
-    double* base[GPMPC_MAXW];         // peer-mapped base of each rank's exchange block (own = local)
-    int world, rank;
-    long long goff;                   // offset (doubles) of this step's gather buffer inside the block
-    int flag_idx;                     // parity * GPMPC_MAXW + rank
-    unsigned long long step;
-    unsigned int* counter;            // local completion counter (zeroed at the start of the step)
-    unsigned int total_blocks;
-};
-
-__global__ void finalize_local_kernel(const double* __restrict__ PMJ, int nblk_mj,
-                                      const double* __restrict__ SQ, int nblk_sq,
-                                      const double* __restrict__ hyp, int hyp_ld, int Nx, int Hc,
-                                      double* __restrict__ G, int slot0, int Htot, int h0,
-                                      const PeerArgs pa, int use_peers)
-{
-    const int a = blockIdx.y, h = blockIdx.x, q = threadIdx.x;   // q in [0, Nx+1]
-    const long long off = (((long long)(slot0 + a)) * Htot + h0 + h) * (Nx + 2);
-    double val = 0.0; int dst = -1;
-    if (q <= Nx) {
-        const double* p = PMJ + (((long long)a * Hc + h) * nblk_mj) * (Nx + 1) + q;
-        double s = 0.0;
-        for (int b = 0; b < nblk_mj; ++b) s += p[(long long)b * (Nx + 1)];
-        val = s; dst = (q == 0) ? 0 : q + 1;
-    } else if (q == Nx + 1) {
-        const double* p = SQ + ((long long)a * Hc + h) * nblk_sq;
-        double s = 0.0;
-        for (int b = 0; b < nblk_sq; ++b) s += p[b];
-        const double sf = hyp[(long long)a * hyp_ld + Nx];
-        val = sf * sf - s; dst = 1;
-    }
-    if (!use_peers) {
-        if (dst >= 0) G[off + dst] = val;
-        return;
-    }
-    if (dst >= 0)
-        for (int r = 0; r < pa.world; ++r) pa.base[r][pa.goff + off + dst] = val;
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(pa.counter, 1u);
-        if (done == pa.total_blocks - 1) {           // every block's stores are fenced: publish
-            __threadfence_system();
-            for (int r = 0; r < pa.world; ++r) {
-                unsigned long long* f = reinterpret_cast<unsigned long long*>(pa.base[r]) + pa.flag_idx;
-                asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(pa.step) : "memory");
-            }
-        }
-    }
-}
-
-// stage 5 (after the all-gather): assemble mean (H,Ny), var (H,Ny), J (H,Ny,Nx) and the
-// covariance: 'ME' diag(var) (gp_functions.py:142); 'TA' diag(var) + J Sigma J^T
-// (build_TA_cov, gp_functions.py:167-171).  sigma_per_point: Sigma is (H,Nx,Nx).
-__global__ void assemble_kernel(const double* __restrict__ G, int Ny, int Nx, int H, int method_ta,
-                                const double* __restrict__ Sigma, int sigma_per_point,
-                                double* __restrict__ mean, double* __restrict__ var,
-                                double* __restrict__ J, double* __restrict__ cov,
-                                const unsigned long long* __restrict__ flags, int world,
-                                unsigned long long step, int* __restrict__ status)
-{
-    extern __shared__ double sh[];          // Jh[Ny][Nx], JS[Ny][Nx], varh[Ny]
-    double* Jh = sh; double* JS = sh + Ny * Nx; double* vh = sh + 2 * Ny * Nx;
-    const int h = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-    if (flags) {      // peer mode: acquire every source rank's flag for this step (bounded spin)
-        if (tid < world) {
-            const long long t0 = clock64();
-            unsigned long long v;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + tid) : "memory");
-                if (v >= step) break;
-                if (clock64() - t0 > 8000000000LL) { *reinterpret_cast<volatile int*>(status) = 1 + tid; break; }   // ~4 s; status lives in mapped host memory
-            } while (true);
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < Ny * Nx; idx += nth) {
-        const int a = idx / Nx, d = idx % Nx;
-        const double v = G[(((long long)a) * H + h) * (Nx + 2) + 2 + d];
-        Jh[idx] = v;
-        if (J) J[((long long)h * Ny + a) * Nx + d] = v;
-    }
-    for (int a = tid; a < Ny; a += nth) {
-        const double* g = G + (((long long)a) * H + h) * (Nx + 2);
-        if (mean) mean[(long long)h * Ny + a] = g[0];
-        if (var) var[(long long)h * Ny + a] = g[1];
-        vh[a] = g[1];
-    }
-    __syncthreads();
-    if (!cov) return;
-    if (method_ta) {
-        const double* Sg = Sigma + (sigma_per_point ? (long long)h * Nx * Nx : 0);
-        for (int idx = tid; idx < Ny * Nx; idx += nth) {
-            const int a = idx / Nx, e = idx % Nx;
-            double s = 0.0;
-            for (int d = 0; d < Nx; ++d) s = fma(Jh[a * Nx + d], Sg[d * Nx + e], s);
-            JS[idx] = s;
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < Ny * Ny; idx += nth) {
-        const int a = idx / Ny, b = idx % Ny;
-        double s = (a == b) ? vh[a] : 0.0;
-        if (method_ta) {
-            double t = 0.0;
-            for (int e = 0; e < Nx; ++e) t = fma(JS[a * Nx + e], Jh[b * Nx + e], t);
-            s += t;
-        }
-        cov[((long long)h * Ny + a) * Ny + b] = s;
-    }
-}
-
 // ---------------------------------------------------------------------------------------
 // a6/a7 analytic NLML gradient, fused with a K rebuild so dK/dtheta is never stored:
 //   dNLL/dtheta = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta)   (R&W eq. 5.9; objective of

@@ -1,0 +1,429 @@
+// Fused predict step (a8-a10, gp_functions.py:111-147, :167-171):  one persistent kernel does
+//   v = L^-1 ks  (fp64 DMMA fed by TMA tensor maps)         -> sum_i v_i^2      (never stored)
+//   var = sf2 - v^T v, mean = ks^T alpha, J                 -> gather records [mean,var,J..]
+//   (multi-GPU) records stored straight into every peer's gather buffer over NVLink, flags published
+//   cov = diag(var) (+ J Sigma J^T)                         -> mean / var / J / cov outputs
+//
+// Scheduling is stream-K: the triangular product's work is the list of BK=16 k-steps of every
+// (output a, 128-column tile jt) pair -- tile jt has (jt+1)*8 steps because L^-1 is lower
+// triangular -- and the persistent grid (2 CTAs per SM) cuts that list into equal contiguous
+// ranges, so every CTA issues the same number of DMMAs regardless of where tile borders fall
+// (the static split-K grid it replaces lost 14 % to the tail at one output per GPU).  A tile cut
+// by a range border is completed by its LAST-ARRIVING contributor: everyone else parks its partial
+// accumulators in a per-CTA slot and bumps the tile's counter; the last one adds the parked
+// partials in contributor order (fixed order => bit-reproducible), squares and row-reduces.
+// The same "last arriver" idea chains the rest of the step: the CTA that finishes an output's last
+// tile builds that output's [mean,var,J] records (and stores them to the peers), the CTA that
+// finishes the last output publishes the peer flags and assembles the covariances.
+// All counters are self-cleaning (reset by their last arriver): no memset between steps.
+#pragma once
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+
+#define GPMPC_MAXW 16
+#define PSK_BN 128
+#define PSK_STAGES 4
+#define PSK_THREADS 256
+
+// Peer ("fused epilogue + all-gather") mode: instead of writing into the local gather buffer and
+// calling ncclAllGather, every rank stores its [mean,var,J] records directly into the gather
+// buffer of EVERY rank (peer pointers mapped with CUDA IPC, NVLink/NVSwitch P2P stores), then
+// publishes a per-source flag on every peer (release at system scope).  The consumer acquires all
+// `world` flags before reading.  Buffers are double-buffered by step parity; in-order streams make
+// that sufficient.
+struct PeerArgs {
+    double* base[GPMPC_MAXW];         // peer-mapped base of each rank's exchange block (own = local)
+    int world, rank;
+    long long goff;                   // offset (doubles) of this step's gather buffer inside the block
+    int flag_idx;                     // parity * GPMPC_MAXW + rank
+    unsigned long long step;
+    long long timeout_clocks;         // consumer gives up (status word, no assembly) after this many clock64 ticks
+};
+
+struct AssembleArgs {
+    const double* G;                  // gather buffer [Ny_pad][H][2+Nx]
+    int Ny, Nx, H, method_ta;
+    const double* Sigma; int sigma_per_point;
+    double *mean, *var, *J, *cov;
+    const unsigned long long* flags;  // peer mode: this step's flag row (world entries), else null
+    int world; unsigned long long step; int* status;
+    long long timeout_clocks;
+};
+
+struct PredictParams {
+    int nloc, nt, Hc;                 // local outputs, 128-column tiles per output, valid rows of this chunk
+    long long T, G;                   // k-steps per output = 4 nt (nt+1), total = nloc * T
+    double* part;                     // [grid][2][BM*128] parked partial accumulators (fragment-major)
+    unsigned int* tile_cnt;           // [nloc*nt]
+    unsigned int* out_cnt;            // [nloc]
+    unsigned int* done_cnt;           // [1]
+    double* SQ;                       // [nloc][64][nt] per-tile sums of squares
+    double* Vout; long long sV; int ldv;     // optional: the solved rows themselves (refinement, GP.covar, append)
+    int finalize;                     // 0: product only (Vout / SQ), 1: build the gather records
+    const double* PMJ; int nblk_mj;   // partial mean / Jacobian sums of ks_mean_jac_kernel
+    const double* hyp; int hyp_ld, Nx;
+    double* Gloc; int slot0, Htot, h0;
+    PeerArgs pa; int use_peers, publish;
+    AssembleArgs as; int do_assemble;
+};
+
+// ---- stage 5: assemble mean (H,Ny), var (H,Ny), J (H,Ny,Nx) and the covariance for test point h:
+// 'ME' diag(var) (gp_functions.py:142); 'TA' diag(var) + J Sigma J^T (build_TA_cov, :167-171).
+__device__ __forceinline__ void assemble_point(const AssembleArgs& A, int h, double* sh, int tid, int nth)
+{
+    const int Ny = A.Ny, Nx = A.Nx, H = A.H;
+    double* Jh = sh; double* JS = sh + Ny * Nx; double* vh = sh + 2 * Ny * Nx;
+    for (int idx = tid; idx < Ny * Nx; idx += nth) {
+        const int a = idx / Nx, d = idx % Nx;
+        const double v = __ldcg(A.G + (((long long)a) * H + h) * (Nx + 2) + 2 + d);
+        Jh[idx] = v;
+        if (A.J) A.J[((long long)h * Ny + a) * Nx + d] = v;
+    }
+    for (int a = tid; a < Ny; a += nth) {
+        const double* g = A.G + (((long long)a) * H + h) * (Nx + 2);
+        const double m = __ldcg(g), v = __ldcg(g + 1);
+        if (A.mean) A.mean[(long long)h * Ny + a] = m;
+        if (A.var) A.var[(long long)h * Ny + a] = v;
+        vh[a] = v;
+    }
+    __syncthreads();
+    if (A.cov) {
+        if (A.method_ta) {
+            const double* Sg = A.Sigma + (A.sigma_per_point ? (long long)h * Nx * Nx : 0);
+            for (int idx = tid; idx < Ny * Nx; idx += nth) {
+                const int a = idx / Nx, e = idx % Nx;
+                double s = 0.0;
+                for (int d = 0; d < Nx; ++d) s = fma(Jh[a * Nx + d], Sg[d * Nx + e], s);
+                JS[idx] = s;
+            }
+            __syncthreads();
+        }
+        for (int idx = tid; idx < Ny * Ny; idx += nth) {
+            const int a = idx / Ny, b = idx % Ny;
+            double s = (a == b) ? vh[a] : 0.0;
+            if (A.method_ta) {
+                double t = 0.0;
+                for (int e = 0; e < Nx; ++e) t = fma(JS[a * Nx + e], Jh[b * Nx + e], t);
+                s += t;
+            }
+            A.cov[((long long)h * Ny + a) * Ny + b] = s;
+        }
+    }
+    __syncthreads();
+}
+
+// peer mode: acquire every source rank's flag for this step; false = a rank never showed up
+__device__ __forceinline__ bool peer_acquire(const AssembleArgs& A, int tid, int* sh_ok)
+{
+    if (!A.flags) return true;
+    if (tid == 0) *sh_ok = 1;
+    __syncthreads();
+    if (tid < A.world) {
+        const long long t0 = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.flags + tid) : "memory");
+            if (v >= A.step) break;
+            if (clock64() - t0 > A.timeout_clocks) {      // status lives in mapped host memory
+                *reinterpret_cast<volatile int*>(A.status) = 1 + tid;
+                *reinterpret_cast<volatile int*>(sh_ok) = 0;
+                break;
+            }
+            __nanosleep(64);
+        } while (true);
+    }
+    __syncthreads();
+    return *reinterpret_cast<volatile int*>(sh_ok) != 0;
+}
+
+// stand-alone assembly (H above one chunk, or after the NCCL all-gather fallback)
+__global__ void __launch_bounds__(128)
+assemble_kernel(const AssembleArgs A)
+{
+    extern __shared__ double sh[];          // Jh[Ny][Nx], JS[Ny][Nx], varh[Ny]
+    __shared__ int ok;
+    if (!peer_acquire(A, threadIdx.x, &ok)) return;
+    for (int h = blockIdx.x; h < A.H; h += gridDim.x) assemble_point(A, h, sh, threadIdx.x, blockDim.x);
+}
+
+struct PskIter { int a, jt, s, ks; };
+
+__device__ __forceinline__ void psk_iter_init(PskIter& it, long long g, long long T)
+{
+    it.a = (int)(g / T);
+    const long long r = g - (long long)it.a * T;               // 4 jt (jt+1) <= r
+    int jt = (int)((sqrt((double)r + 1.0) - 1.0) * 0.5);
+    while (4LL * jt * (jt + 1) > r) --jt;
+    while (4LL * (jt + 1) * (jt + 2) <= r) ++jt;
+    it.jt = jt; it.s = (int)(r - 4LL * jt * (jt + 1)); it.ks = (jt + 1) * 8;
+}
+__device__ __forceinline__ void psk_iter_next(PskIter& it, int nt)
+{
+    if (++it.s == it.ks) {
+        it.s = 0;
+        if (++it.jt == nt) { it.jt = 0; ++it.a; }
+        it.ks = (it.jt + 1) * 8;
+    }
+}
+
+// [mean, var, J_0..] records of output a for the chunk's test points (one warp per point):
+//   mean, J from the partial sums of ks_mean_jac_kernel; var = sf2 - sum_jt SQ (gp_functions.py:125-126,136)
+__device__ __forceinline__ void psk_finalize_output(const PredictParams& p, int a, int warp, int nwarps, int lane)
+{
+    const int Nx = p.Nx;
+    for (int h = warp; h < p.Hc; h += nwarps) {
+        const double* sq = p.SQ + ((long long)a * 64 + h) * p.nt;
+        double sv = 0.0;
+        for (int j = lane; j < p.nt; j += 32) sv += __ldcg(sq + j);
+        sv = warp_sum(sv);
+        const long long off = (((long long)(p.slot0 + a)) * p.Htot + p.h0 + h) * (Nx + 2);
+        auto put = [&](int d, double v) {
+            if (!p.use_peers) { p.Gloc[off + d] = v; return; }
+            for (int r = 0; r < p.pa.world; ++r) p.pa.base[r][p.pa.goff + off + d] = v;
+        };
+        for (int q = lane; q <= Nx; q += 32) {                 // q = 0: mean, q >= 1: J_{q-1}  (NX_MAX = 32: <= 2 rounds)
+            const double* pm = p.PMJ + (((long long)a * p.Hc + h) * p.nblk_mj) * (Nx + 1) + q;
+            double sm = 0.0;
+            for (int b = 0; b < p.nblk_mj; ++b) sm += pm[(long long)b * (Nx + 1)];
+            put(q == 0 ? 0 : q + 1, sm);
+        }
+        if (lane == 31) {
+            const double sf = p.hyp[(long long)a * p.hyp_ld + Nx];
+            put(1, sf * sf - sv);
+        }
+    }
+    if (p.use_peers) __threadfence_system(); else __threadfence();
+}
+
+// after an output's records are written: the CTA that completes the step's last output publishes
+// the peer flags and (optionally) assembles.  Must be called by every thread of the CTA.
+__device__ __forceinline__ void psk_step_tail(const PredictParams& p, double* sh, int tid, int nth,
+                                              unsigned int* s_flag, int* s_ok)
+{
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int old = atomicAdd(p.done_cnt, 1u);
+        const unsigned int last = (old == (unsigned int)(p.nloc - 1)) ? 1u : 0u;
+        if (last) *p.done_cnt = 0u;
+        *s_flag = last;
+    }
+    __syncthreads();
+    if (*s_flag == 0u) return;
+    if (p.finalize && p.use_peers && p.publish && tid == 0) {
+        __threadfence_system();
+        for (int r = 0; r < p.pa.world; ++r) {
+            unsigned long long* f = reinterpret_cast<unsigned long long*>(p.pa.base[r]) + p.pa.flag_idx;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(p.pa.step) : "memory");
+        }
+    }
+    if (p.do_assemble) {
+        __threadfence();
+        if (peer_acquire(p.as, tid, s_ok))
+            for (int h = 0; h < p.as.H; ++h) assemble_point(p.as, h, sh, tid, nth);
+    }
+}
+
+// refinement path: the solved rows were corrected outside the product (v = v1 + Li r), so the
+// squared norms are taken from V itself; then the common finalize / publish / assemble tail.
+// grid (nt, Hc, nloc): SQ[a][h][jt] = sum of squares of the 128 columns of tile jt
+__global__ void __launch_bounds__(128)
+sq_rows_kernel(const double* __restrict__ V, int ldv, long long sV, double* __restrict__ SQ, int nt)
+{
+    __shared__ double red[4];
+    const int jt = blockIdx.x, h = blockIdx.y, a = blockIdx.z;
+    const double v = V[(long long)a * sV + (long long)h * ldv + jt * 128 + threadIdx.x];
+    const double s = warp_sum(v * v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) SQ[((long long)a * 64 + h) * nt + jt] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+__global__ void __launch_bounds__(PSK_THREADS)
+finalize_kernel(const PredictParams p)
+{
+    extern __shared__ double sh[];
+    __shared__ unsigned int s_flag;
+    __shared__ int s_ok;
+    psk_finalize_output(p, blockIdx.x, threadIdx.x >> 5, PSK_THREADS / 32, threadIdx.x & 31);
+    psk_step_tail(p, sh, threadIdx.x, PSK_THREADS, &s_flag, &s_ok);
+}
+
+template <int BM>
+__global__ void __launch_bounds__(PSK_THREADS, 2)
+predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB)
+{
+    constexpr int BK = GEMM_BK, BN = PSK_BN, STAGES = PSK_STAGES;
+    constexpr int WTN = BN / 8, MF = BM / 8, NF = WTN / 8;        // 8 warps side by side: 16 columns each
+    constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;           // doubles, 128-byte rows, 128B swizzle
+    constexpr uint32_t STAGE_TX = (BM + BN) * BK * 8;
+    static_assert(BM % 8 == 0 && BM >= 8 && BM <= 64, "BM");
+
+    extern __shared__ __align__(16) double smem_raw[];
+    double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    double* As = smem;
+    double* Bs = smem + STAGES * A_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
+    __shared__ double red[8][64];
+    __shared__ unsigned int s_flag;
+    __shared__ int s_ok;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const long long C = gridDim.x, c = blockIdx.x;
+    const long long g0 = p.G * c / C;
+    const int nsteps = (int)(p.G * (c + 1) / C - g0);           // this CTA's share of the k-step list
+    if (nsteps <= 0) return;
+
+    // producer state lives in shared memory: only thread 0 touches it, so it costs no registers
+    __shared__ PskIter s_pit;
+    __shared__ int s_pg;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&]() {               // thread 0: TMA loads of step s_pg into stage s_pg % STAGES
+        PskIter it = s_pit;
+        const int s = s_pg % STAGES;
+        mbar_arrive_expect_tx(full + s, STAGE_TX);
+        tma_tile_g2s_3d(As + s * A_STAGE, &tmA, it.s * BK, 0, it.a, full + s);
+        tma_tile_g2s_3d(Bs + s * B_STAGE, &tmB, it.s * BK, it.jt * BN, it.a, full + s);
+        psk_iter_next(it, p.nt);
+        s_pit = it;
+        s_pg = s_pg + 1;
+    };
+    if (tid == 0) {
+        PskIter it;
+        psk_iter_init(it, g0, p.T);
+        s_pit = it; s_pg = 0;
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (s_pg < nsteps) issue();
+    }
+
+    PskIter cit;
+    psk_iter_init(cit, g0, p.T);
+    const int kperm_hi = 4 * (t >> 1), kpar = t & 1;
+    int i = 0;
+    while (i < nsteps) {
+        const int a = cit.a, jt = cit.jt, s_begin = cit.s, ksteps = cit.ks;
+        const int seg = min(ksteps - s_begin, nsteps - i);
+        double acc[MF][NF][2];
+#pragma unroll
+        for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NF; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+        for (int q = 0; q < seg; ++q, ++i) {
+            const int s = i % STAGES;
+            mbar_wait(full + s, (uint32_t)((i / STAGES) & 1));
+            __syncthreads();                              // everyone is done with the stage refilled below
+            if (tid == 0 && s_pg < nsteps) issue();
+            const double* as = As + s * A_STAGE + g * 16 + kpar;
+            const double* bs = Bs + s * B_STAGE + (warp * WTN + g) * 16 + kpar;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                const int coff = (((kk + kperm_hi) ^ g) << 1);
+                double av[MF], bv[NF];
+#pragma unroll
+                for (int mi = 0; mi < MF; ++mi) av[mi] = as[mi * 8 * 16 + coff];
+#pragma unroll
+                for (int ni = 0; ni < NF; ++ni) bv[ni] = bs[ni * 8 * 16 + coff];
+#pragma unroll
+                for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NF; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+            }
+        }
+        cit.s = s_begin + seg - 1;
+        psk_iter_next(cit, p.nt);
+
+        // ---- tile fix-up: a tile cut by a range border is finished by its last-arriving contributor
+        bool have_tile = true;
+        if (seg != ksteps) {
+            const long long tg0 = (long long)a * p.T + 4LL * jt * (jt + 1), tg1 = tg0 + ksteps;
+            const int c_first = (int)(((tg0 + 1) * C - 1) / p.G), c_last = (int)((tg1 * C - 1) / p.G);
+            double* mine = p.part + ((long long)c * 2 + (s_begin == 0 ? 1 : 0)) * (BM * BN);
+#pragma unroll
+            for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NF; ++ni)
+                    __stcg(reinterpret_cast<double2*>(mine + ((mi * NF + ni) * PSK_THREADS + tid) * 2),
+                           make_double2(acc[mi][ni][0], acc[mi][ni][1]));
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                unsigned int* cnt = p.tile_cnt + (long long)a * p.nt + jt;
+                const unsigned int old = atomicAdd(cnt, 1u);
+                const unsigned int last = (old == (unsigned int)(c_last - c_first)) ? 1u : 0u;
+                if (last) *cnt = 0u;                      // self-cleaning: every contributor has arrived
+                s_flag = last;
+            }
+            __syncthreads();
+            have_tile = s_flag != 0u;
+            if (have_tile) {
+                __threadfence();
+#pragma unroll
+                for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NF; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+                for (int cc = c_first; cc <= c_last; ++cc) {          // contributor (= ascending k) order
+                    const double* src = p.part + ((long long)cc * 2 + (cc == c_first ? 1 : 0)) * (BM * BN);
+#pragma unroll
+                    for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < NF; ++ni) {
+                            const double2 v = __ldcg(reinterpret_cast<const double2*>(src + ((mi * NF + ni) * PSK_THREADS + tid) * 2));
+                            acc[mi][ni][0] += v.x; acc[mi][ni][1] += v.y;
+                        }
+                }
+            }
+        }
+        if (!have_tile) continue;
+
+        // ---- complete tile: optional store of the solved rows, squared row norms of this column tile
+        if (p.Vout) {
+#pragma unroll
+            for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NF; ++ni) {
+                    const int row = mi * 8 + g, col = jt * BN + warp * WTN + ni * 8 + 2 * t;
+                    *reinterpret_cast<double2*>(p.Vout + (long long)a * p.sV + (long long)row * p.ldv + col) =
+                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                }
+        }
+#pragma unroll
+        for (int mi = 0; mi < MF; ++mi) {
+            double r = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < NF; ++ni) { r = fma(acc[mi][ni][0], acc[mi][ni][0], r); r = fma(acc[mi][ni][1], acc[mi][ni][1], r); }
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            if (t == 0) red[warp][mi * 8 + g] = r;
+        }
+        __syncthreads();
+        if (tid < BM) {
+            double r = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) r += red[w][tid];
+            __stcg(p.SQ + ((long long)a * 64 + tid) * p.nt + jt, r);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int* cnt = p.out_cnt + a;
+            const unsigned int old = atomicAdd(cnt, 1u);
+            const unsigned int last = (old == (unsigned int)(p.nt - 1)) ? 1u : 0u;
+            if (last) *cnt = 0u;
+            s_flag = last;
+        }
+        __syncthreads();
+        if (s_flag == 0u) continue;
+
+        // ---- this CTA completed output a: build its records; last output => publish / assemble
+        __threadfence();
+        if (p.finalize) psk_finalize_output(p, a, warp, PSK_THREADS / 32, lane);
+        psk_step_tail(p, smem, tid, PSK_THREADS, &s_flag, &s_ok);
+    }
+}

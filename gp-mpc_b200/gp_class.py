@@ -152,6 +152,10 @@ class GP:
             if info[k] == 1:                         # optimize.py:486
                 print("K matrix is not positive definit, adding jitter!")
         self.__invK = None
+        # ranks factorise independently (a jitter retry on one rank can take seconds at large N):
+        # line them up again before the first predict step's peer exchange starts its timeout clock
+        if self.__comm.world > 1:
+            self.__comm.barrier()
 
     @property
     def engine(self):
@@ -256,7 +260,16 @@ class GP:
         if gp_method not in _GPU_METHODS:
             raise NotImplementedError("gp_method %r is not implemented by the B200 engine "
                                       "(available: 'ME', 'TA', 'EM')" % gp_method)
+        if gp_method == 'EM' and self.__sharded_outputs():
+            # exact moment matching couples every pair of outputs (gp_functions.py:394-412): it
+            # needs all Ny factors on one GPU, which the by-output sharding does not provide
+            raise NotImplementedError("gp_method 'EM' needs all outputs on one GPU; this GP is sharded by "
+                                      "output over %d ranks (use 'TA'/'ME', or build the GP with a "
+                                      "single-process Comm)" % self.__comm.world)
         self.__gp_method = gp_method
+
+    def __sharded_outputs(self):
+        return self.__comm.world > 1 and getattr(self, '_GP__mode', 'outputs') == 'outputs'
 
     def __predict_std(self, Z, Sigma, method, want_cov=True, want_jac=True):
         """Batched predict in the GP's standardised space.  Z:(H,Nx)."""
@@ -283,6 +296,8 @@ class GP:
             x = self.standardize(x, self.__meanX, self.__stdX)
             u = self.standardize(u, self.__meanU, self.__stdU)
         Z = np.hstack([x, u])
+        if cov is None and method in ('TA', 'EM'):
+            cov = np.zeros((self.__Nx, self.__Nx))      # no input uncertainty: TA reduces to diag(var)
         mean, var, c, _ = self.__predict_std(Z, cov if method in ('TA', 'EM') else None, method, True, False)
         if self.__normalize:
             mean = self.inverse_mean(mean, self.__meanY, self.__stdY)
@@ -318,7 +333,9 @@ class GP:
         u = np.asarray(u, dtype=np.float64).reshape(-1, self.__Nu)
         Nt = u.shape[0]
         initVar = self.__hyper[:, Nx + 1] ** 2
-        methods = ['EM', 'TA', 'ME'] if methods is None else list(methods)
+        if methods is None:                             # gp_class.py:747 default; 'EM' only where it can run
+            methods = ['TA', 'ME'] if self.__sharded_outputs() else ['EM', 'TA', 'ME']
+        methods = list(methods)
         mean = np.zeros((len(methods), Nt + 1, Ny))
         var = np.zeros((len(methods), Nt + 1, Ny))
         covar = np.eye(Nx) * 1e-6                       # shared across methods, as in the reference
@@ -442,7 +459,12 @@ class GP:
             Ys = self.standardize(Y_new, self.__meanY, self.__stdY)
             Xs = self.standardize(X_new, self.__meanZ, self.__stdZ)
         for k in range(Xs.shape[0]):
-            if not self.__engine.append(Xs[k], Ys[k]):
+            ok = self.__engine.append(Xs[k], Ys[k])
+            if self.__comm.world > 1:
+                # the fallback below runs collectives (engine rebuild): the decision must be collective
+                # too -- a rank that alone lost positive definiteness would otherwise hang the others
+                ok = all(self.__comm.allgather_object(bool(ok)))
+            if not ok:
                 self.__X = np.vstack([self.__X, Xs[k:]])
                 self.__Y = np.vstack([self.__Y, Ys[k:]])
                 self.__N = self.__X.shape[0]
@@ -494,7 +516,10 @@ class GP:
     def discrete_linearize(self, x0, u0, cov0):
         """ Linearize the GP around the operating point  x[k+1] = Ax[k] + Bu[k]
         (reference gp_class.py:647-661): Jacobian of the predicted mean in standardised
-        space, inputs standardised when normalize, outputs not rescaled. """
+        space, inputs standardised when normalize, outputs not rescaled.  The reference
+        differentiates the ACTIVE method's mean; for 'ME'/'TA' that is the posterior-mean Jacobian
+        returned here, for 'EM' (mean depends on the input covariance) the reference's A, B differ --
+        this engine always linearises the 'ME' mean. """
         x0 = np.asarray(x0, dtype=np.float64).reshape(-1)
         u0 = np.asarray(u0, dtype=np.float64).reshape(-1)
         if self.__normalize:

@@ -224,6 +224,47 @@ def postfit(X, Y, hyper, lapack_general_solve=True):
     return dict(chol=chol, alpha=alpha, invK=invK, jitter=jit)
 
 
+def factor_large(X, y, hyper_a):
+    """Post-fit block ``optimize.py:476-494`` for ONE output at the BASELINE sizes
+    (N = 4096 ... 16384), where ``postfit`` (Nx full-size temporaries per K, dense invK) is
+    too slow for a test: K through ``covSEard_blas`` (the reference's expansion with the
+    per-dimension rank-1 updates folded into one BLAS product), ``np.linalg.cholesky`` with
+    the single 1e-8 jitter retry (:483-488), alpha by true triangular solves (q11) and the
+    NLL of ``optimize.py:352-355``.  invK is not formed.
+    Returns dict(chol, alpha, nll, jitter)."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    hyper_a = np.asarray(hyper_a, dtype=np.float64)
+    n, D = X.shape
+    K = covSEard_blas(X, X, hyper_a[:D], hyper_a[D] ** 2)
+    K[np.diag_indices(n)] += hyper_a[D + 1] ** 2
+    K = (K + K.T) * 0.5                                        # :482
+    L, jit = chol_with_jitter(K)
+    del K
+    invLy = _solve_tri(L, y, lower=True, check_finite=False)
+    alpha = _solve_tri(L, invLy, lower=True, trans='T', check_finite=False)
+    nll = 0.5 * float(np.dot(y, alpha)) + float(np.sum(np.log(np.abs(np.diag(L)))))
+    return dict(chol=L, alpha=alpha, nll=nll, jitter=jit)
+
+
+def predict_large(X, hyper_a, alpha_a, L_a, Z):
+    """Numeric predict of ONE output for a batch (``gp_functions.py:111-147``; the numeric twin
+    ``GP.covar`` ``gp_class.py:353-381``) with BLAS-folded ks and Jacobian sums, for the
+    BASELINE sizes: mean (H,), var (H,), J (H,Nx)."""
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+    Nx = X.shape[1]
+    ell = np.asarray(hyper_a[:Nx], dtype=np.float64); sf2 = float(hyper_a[Nx]) ** 2
+    ks = covSEard(X, Z, ell, sf2) if X.shape[0] * Z.shape[0] <= (1 << 22) else covSEard_blas(X, Z, ell, sf2)
+    mean = ks.T @ alpha_a
+    v = _solve_tri(L_a, ks, lower=True, check_finite=False)
+    var = sf2 - np.sum(v * v, axis=0)
+    w = ks * alpha_a[:, None]                                  # (N,H)
+    # J[h,d] = sum_i w_ih (X_id - z_hd)/ell_d^2 = ((X^T w)_dh - z_hd sum_i w_ih)/ell_d^2
+    J = ((X.T @ w).T - Z * np.sum(w, axis=0)[:, None]) / ell[None, :] ** 2
+    return mean, var, J
+
+
 # ----------------------------------------------------------------------------
 # a8/a9/a10  posterior mean / variance / Jacobian / Taylor covariance
 # ----------------------------------------------------------------------------

@@ -66,5 +66,18 @@ class OracleEngine:
             cov = orc.ta_cov(v, J, Sigma) if (method == 1 and Sigma is not None) else orc.me_cov(v)
         return m, v, cov, (J if want_jac else None)
 
+    # rank-1 append stand-in: refits with the oracle; `fail_on` = (rank, N) simulates ONE rank losing
+    # positive definiteness (what gpmpc_append reports as GPMPC_ERR_NOTPD -> Engine.append False)
+    fail_on = None
+
+    def append(self, x_new, y_new):
+        if OracleEngine.fail_on is not None and (self.rank, self.N) == tuple(OracleEngine.fail_on):
+            return False
+        self.X = np.vstack([self.X, np.asarray(x_new).reshape(1, -1)])
+        self.Y = np.vstack([self.Y, np.asarray(y_new).reshape(1, -1)])
+        self.N += 1
+        self.factorize()
+        return True
+
     def close(self):
         self.closed = True

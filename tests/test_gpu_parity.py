@@ -142,10 +142,15 @@ def test_predict_synthetic_vs_oracle(N, Nx, Ny, H):
     Sg = np.stack([p['Sigma'] * (1 + 0.1 * h) for h in range(H)])
     _, _, cov_pp, _ = eng.predict(p['Z'], Sg, _L().METHOD_TA)
     assert relinf(cov_pp, orc.ta_cov(vo, Jo, Sg)) < TOL
-    # split-K chunking must not change the result beyond rounding
-    eng.set_option('ksplit', 128)
-    _, var_s, _, _ = eng.predict(p['Z'], p['Sigma'], _L().METHOD_TA)
-    assert relinf(var_s, var) < 1e-9
+    # the stream-K partition (persistent grid size) must not change the result beyond rounding,
+    # and a fixed partition is bit-reproducible (parked partials are added in contributor order)
+    mean_b, var_b, cov_b, jac_b = eng.predict(p['Z'], p['Sigma'], _L().METHOD_TA)
+    assert np.array_equal(var_b, var) and np.array_equal(mean_b, mean) and np.array_equal(cov_b, cov)
+    for ctas in (1, 7, 1000):
+        eng.set_option('predict_ctas', ctas)
+        mean_s, var_s, cov_s, jac_s = eng.predict(p['Z'], p['Sigma'], _L().METHOD_TA)
+        assert relinf(var_s, var) < 1e-9 and np.array_equal(mean_s, mean) and np.array_equal(jac_s, jac)
+        assert relinf(cov_s, cov) < 1e-9
     eng.close()
 
 
@@ -203,9 +208,88 @@ def test_full_size_properties_n16384():
     eng.set_option('refine', 1)
     _, var_r, _, _ = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
     assert relinf(var_r, var_t) < 1e-6
-    eng.set_option('refine', 0); eng.set_option('ksplit', 4096)
+    eng.set_option('refine', 0); eng.set_option('predict_ctas', 100)
     _, var_k, _, _ = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
     assert relinf(var_k, var_t) < 1e-8
+    eng.close()
+
+
+# ------------------------------------------------------------------ BASELINE sizes against an independent CPU factor
+def test_c3_full_size_vs_oracle():
+    """BASELINE config C3 (N=4096, Nx=8, Ny=6, H=30, TA) at its stated size: every output against
+    an independent CPU Cholesky (np.linalg.cholesky + triangular solves, oracle factor_large /
+    predict_large): chol <= 1e-9, mean / var / J / cov <= 1e-6 (batch-inf-norm relative)."""
+    N, Nx, Ny, H = 4096, 8, 6, 30
+    p = orc.synthetic_problem(N, Nx, Ny, config_id=3, H=H)
+    eng, info = _fit_engine(p['X'], p['Y'], p['hyper'])
+    assert not info.any()
+    L = _L()
+    mean, var, cov, jac = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
+    mo = np.zeros((H, Ny)); vo = np.zeros((H, Ny)); Jo = np.zeros((H, Ny, Nx))
+    for a in range(Ny):
+        f = orc.factor_large(p['X'], p['Y'][:, a], p['hyper'][a])
+        assert not f['jitter']
+        assert relinf(eng.get(L.GET_CHOL, a), f['chol']) < 1e-9
+        assert relinf(eng.get(L.GET_ALPHA, a), f['alpha']) < 1e-6
+        assert eng.get(L.GET_LOGDET, a)[0] == pytest.approx(2 * np.sum(np.log(np.diag(f['chol']))), rel=1e-10)
+        mo[:, a], vo[:, a], Jo[:, a] = orc.predict_large(p['X'], p['hyper'][a], f['alpha'], f['chol'], p['Z'])
+    co = orc.ta_cov(vo, Jo, p['Sigma'])
+    assert relinf(mean, mo) < TOL and relinf(var, vo) < TOL and relinf(jac, Jo) < TOL and relinf(cov, co) < TOL
+    # cancellation-aware view (SURVEY 8d): |dvar| / sf2
+    assert np.abs(var - vo).max() < 1e-9
+    eng.close()
+
+
+def test_c4_nlml_and_gradient_at_n8192():
+    """BASELINE config C4 (N=8192, Nx=8, one output): NLL <= 1e-9 relative vs the CPU restatement
+    of calc_NLL_numpy (optimize.py:322-356) and the analytic gradient vs central differences of
+    that NLL on three components (one length scale, sf, sn) <= 1e-5."""
+    N, Nx = 8192, 8
+    p = orc.synthetic_problem(N, Nx, 1, config_id=4)
+    eng = _engine(N, Nx, 1); eng.set_data(p['X'], p['Y'])
+    th = p['hyper'][0].copy(); th[:Nx] *= 0.8; th[Nx] = 0.9; th[Nx + 1] = 8e-3
+    nll, g = eng.nlml(0, th, grad=True)
+    y = p['Y'][:, 0]
+    ref = orc.factor_large(p['X'], y, th)['nll']
+    assert nll == pytest.approx(ref, rel=1e-9)
+    for j in (2, Nx, Nx + 1):
+        h = 1e-5 * max(1.0, abs(th[j])) if j <= Nx else 1e-5 * th[j]
+        tp = th.copy(); tp[j] += h
+        tm = th.copy(); tm[j] -= h
+        fd = (orc.factor_large(p['X'], y, tp)['nll'] - orc.factor_large(p['X'], y, tm)['nll']) / (2 * h)
+        assert abs(g[j] - fd) <= 1e-5 * max(abs(fd), np.abs(g).max() * 1e-2), (j, g[j], fd)
+    # the GPU's own NLL differences agree with its gradient too (same stencil, GPU evaluations)
+    j = 0
+    h = 1e-5 * th[j]
+    tp = th.copy(); tp[j] += h
+    tm = th.copy(); tm[j] -= h
+    fd_gpu = (eng.nlml(0, tp, grad=False) - eng.nlml(0, tm, grad=False)) / (2 * h)
+    assert abs(g[j] - fd_gpu) <= 1e-5 * max(abs(fd_gpu), np.abs(g).max() * 1e-2)
+    eng.close()
+
+
+def test_c5_full_size_vs_independent_cholesky():
+    """BASELINE config C5's per-GPU problem (N=16384, Nx=10, H=50, one output, TA) against an
+    INDEPENDENT CPU factor (np.linalg.cholesky of the reference's expansion-form K + triangular
+    solves): chol <= 1e-9, mean / var / J / cov <= 1e-6."""
+    N, Nx, H = 16384, 10, 50
+    p = orc.synthetic_problem(N, Nx, 1, config_id=5, H=H)
+    eng, info = _fit_engine(p['X'], p['Y'], p['hyper'])
+    assert not info.any()
+    L = _L()
+    mean, var, cov, jac = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
+    f = orc.factor_large(p['X'], p['Y'][:, 0], p['hyper'][0])
+    assert not f['jitter']
+    mo, vo, Jo = orc.predict_large(p['X'], p['hyper'][0], f['alpha'], f['chol'], p['Z'])
+    chol = eng.get(L.GET_CHOL, 0)
+    assert relinf(chol, f['chol']) < 1e-9
+    del chol
+    assert relinf(eng.get(L.GET_ALPHA, 0), f['alpha']) < 1e-5          # alpha is cond(K)*eps limited
+    assert eng.get(L.GET_LOGDET, 0)[0] == pytest.approx(2 * np.sum(np.log(np.diag(f['chol']))), rel=1e-10)
+    co = orc.ta_cov(vo[:, None], Jo[:, None, :], p['Sigma'])
+    assert relinf(mean[:, 0], mo) < TOL and relinf(var[:, 0], vo) < TOL
+    assert relinf(jac[:, 0], Jo) < TOL and relinf(cov, co) < TOL
+    assert np.abs(var[:, 0] - vo).max() < 1e-9
     eng.close()
 
 

@@ -42,6 +42,24 @@ def _worker(rank, world, port, case, q):
         hy = np.column_stack([gp2.get_hyper_parameters()['length_scale'],
                               np.sqrt(gp2.get_hyper_parameters()['signal_var']),
                               np.sqrt(gp2.get_hyper_parameters()['noise_var'])])
+        extra = {}
+        if case == 'outputs':
+            # only rank 1 "loses positive definiteness" on the 2nd appended point; the
+            # refit fallback is a collective, so the decision must be collective (no hang, same N)
+            OracleEngine.fail_on = (1, 41)
+            rng = np.random.default_rng(3)
+            Xn = rng.standard_normal((3, Nx)); Yn = rng.standard_normal((3, Ny))
+            gp.append_data(Xn, Yn)
+            OracleEngine.fail_on = None
+            extra['N_after'] = gp.get_size()[0]
+            extra['chol_after'] = gp.get_chol()
+            extra['Xn'], extra['Yn'] = Xn, Yn
+            try:
+                gp.set_method('EM')
+                extra['em'] = 'accepted'
+            except NotImplementedError:
+                extra['em'] = 'rejected'
+        info.update(extra)
         q.put((rank, info, mean, cov, chol, hy))
     finally:
         dist.destroy_process_group()
@@ -79,3 +97,10 @@ def test_two_ranks(case):
     # and equal to what one process fits (rank-local fits are independent per output)
     for a in range(p['Y'].shape[1]):
         assert orc.calc_NLL(res[0][5][a], p['X'], p['Y'][:, a]) < orc.calc_NLL(orc.train_bounds_init(p['X'], p['Y'][:, a])[1], p['X'], p['Y'][:, a])
+    if case == 'outputs':
+        for r in res:
+            assert r[1]['N_after'] == 43 and r[1]['em'] == 'rejected'
+        Xa = np.vstack([p['X'], res[0][1]['Xn']]); Ya = np.vstack([p['Y'], res[0][1]['Yn']])
+        post = orc.postfit(Xa, Ya, p['hyper'], lapack_general_solve=False)
+        for r in res:
+            np.testing.assert_allclose(r[1]['chol_after'], post['chol'], rtol=1e-12, atol=1e-14)

@@ -165,3 +165,23 @@ def test_train_small_problem_recovers_low_nll():
     out = orc.train_gp(p['X'], p['Y'])
     _, init = orc.train_bounds_init(p['X'], p['Y'][:, 0])
     assert orc.calc_NLL(out['hyper'][0], p['X'], p['Y'][:, 0]) < orc.calc_NLL(init, p['X'], p['Y'][:, 0])
+
+
+def test_large_size_helpers_match_the_restatement():
+    """factor_large / predict_large (BLAS-folded K, no invK -- used by the N >= 4096 GPU parity
+    tests) agree with postfit / gp_mean_var / gp_mean_jac / calc_NLL, which are pinned above."""
+    p = orc.synthetic_problem(700, 6, 2, config_id=9, H=9)
+    post = orc.postfit(p['X'], p['Y'], p['hyper'], lapack_general_solve=False)
+    mo, vo = orc.gp_mean_var(p['X'], p['hyper'], post['alpha'], post['chol'], p['Z'])
+    Jo = orc.gp_mean_jac(p['X'], p['hyper'], post['alpha'], p['Z'])
+    for a in range(2):
+        f = orc.factor_large(p['X'], p['Y'][:, a], p['hyper'][a])
+        assert relinf(f['chol'], post['chol'][a]) < 1e-11
+        assert relinf(f['alpha'], post['alpha'][a]) < 1e-8
+        assert f['nll'] == pytest.approx(orc.calc_NLL(p['hyper'][a], p['X'], p['Y'][:, a]), rel=1e-9)   # y.alpha and logdet cancel
+        m, v, J = orc.predict_large(p['X'], p['hyper'][a], f['alpha'], f['chol'], p['Z'])
+        assert relinf(m, mo[:, a]) < 1e-9 and relinf(v, vo[:, a]) < 1e-8 and relinf(J, Jo[:, a]) < 1e-9
+    for name in ('tank', 'car'):
+        m = load_fixture(name)
+        f = orc.factor_large(m['X'], m['Y'][:, 0], m['hyper'][0])
+        assert relinf(f['chol'], m['chol'][0]) < (1e-10 if name == 'tank' else 2e-9)   # the reference's stored factor
