@@ -34,6 +34,8 @@ SYMBOLS = [
     ('gpmpc_factorize', C.c_int, [_H, C.c_double, _ip]),
     ('gpmpc_nlml', C.c_int, [_H, C.c_int, _dp, _dp, _dp]),
     ('gpmpc_predict', C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]),
+    ('gpmpc_predict_grad', C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    ('gpmpc_get_size', C.c_int, [_H, _ip, _ip, _ip]),
     ('gpmpc_append', C.c_int, [_H, _dp, _dp]),
     ('gpmpc_posterior_cov', C.c_int, [_H, C.c_int, _dp, _dp]),
     ('gpmpc_predict_device', C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
@@ -47,7 +49,24 @@ SYMBOLS = [
     ('gpmpc_stream', C.c_void_p, [_H]),
     ('gpmpc_synchronize', C.c_int, [_H]),
     ('gpmpc_profile', C.c_int, [_H, C.c_int, C.c_int, C.c_int, _dp]),
+    ('gpmpc_profile_balance', C.c_int, [_H, C.c_int, _dp]),
+    ('gpmpc_profile_leaf', C.c_int, [_H, _dp]),
 ]
+
+_ll = C.c_longlong
+_llp = C.POINTER(C.c_longlong)
+_dpp = C.POINTER(_dp)
+# include/gpmpc_casadi.h: the CasADi `external` family (function + its Jacobian)
+for _f in ('gp_b200', 'jac_gp_b200'):
+    SYMBOLS += [
+        (_f + '_n_in', _ll, []), (_f + '_n_out', _ll, []),
+        (_f + '_name_in', C.c_char_p, [_ll]), (_f + '_name_out', C.c_char_p, [_ll]),
+        (_f + '_sparsity_in', _llp, [_ll]), (_f + '_sparsity_out', _llp, [_ll]),
+        (_f + '_work', C.c_int, [_llp, _llp, _llp, _llp]),
+        (_f, C.c_int, [_dpp, _dpp, _llp, _dp, C.c_int]),
+    ]
+SYMBOLS += [('gp_b200_bind', C.c_int, [_H, C.c_int, C.c_int]), ('gp_b200_unbind', None, []),
+            ('gp_b200_incref', None, []), ('gp_b200_decref', None, [])]
 
 _lib = None
 
@@ -188,6 +207,27 @@ class Engine:
                                            _ptr(mean), _ptr(var), _ptr(cov), _ptr(jac)))
         return mean, var, cov, jac
 
+    def predict_grad(self, Z, Sigma=None, method=METHOD_TA, want_hess=False):
+        """Predict + first derivatives w.r.t. the test inputs (gpmpc_predict_grad).
+        Returns dict(mean (H,Ny), var, cov (H,Ny,Ny), jac = dmean_dz (H,Ny,Nx), dvar_dz (H,Ny,Nx),
+        dcov_dz (H,Ny,Ny,Nx)[, hess (H,Ny,Nx,Nx)])."""
+        Z = _f64(Z).reshape(-1, self.Nx)
+        H = Z.shape[0]
+        spp = 0
+        if Sigma is not None:
+            Sigma = _f64(Sigma)
+            spp = 1 if Sigma.ndim == 3 else 0
+            assert Sigma.shape == ((H, self.Nx, self.Nx) if spp else (self.Nx, self.Nx))
+        out = dict(mean=np.empty((H, self.Ny)), var=np.empty((H, self.Ny)), cov=np.empty((H, self.Ny, self.Ny)),
+                   jac=np.empty((H, self.Ny, self.Nx)), dvar_dz=np.empty((H, self.Ny, self.Nx)),
+                   dcov_dz=np.empty((H, self.Ny, self.Ny, self.Nx)))
+        if want_hess:
+            out['hess'] = np.empty((H, self.Ny, self.Nx, self.Nx))
+        self._check(self.lib.gpmpc_predict_grad(self.h, int(method), H, _ptr(Z), _ptr(Sigma), spp, _ptr(out['mean']),
+                                                _ptr(out['var']), _ptr(out['cov']), _ptr(out['jac']), _ptr(out['dvar_dz']),
+                                                _ptr(out['dcov_dz']), _ptr(out.get('hess'))))
+        return out
+
     def append(self, x_new, y_new):
         """Rank-1 append of one training point; returns False when the padded capacity is full
         or positive definiteness is lost (caller refits), True on success."""
@@ -240,6 +280,16 @@ class Engine:
 
     def synchronize(self):
         self._check(self.lib.gpmpc_synchronize(self.h))
+
+    def profile_leaf(self):
+        out = np.zeros(15)
+        self._check(self.lib.gpmpc_profile_leaf(self.h, _ptr(out)))
+        return out
+
+    def profile_balance(self, H):
+        out = np.zeros(4)
+        self._check(self.lib.gpmpc_profile_balance(self.h, int(H), _ptr(out)))
+        return dict(zip(('min_us', 'max_us', 'mean_us', 'span_us'), out))
 
     def profile(self, what, n=0, reps=5):
         ms = C.c_double(0.0)

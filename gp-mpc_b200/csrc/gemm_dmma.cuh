@@ -260,6 +260,13 @@ __device__ __forceinline__ void tma_tile_g2s_3d(void* smem_dst, const CUtensorMa
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_tile_g2s_3d_hint(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;\n"
+                 :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
 __global__ void __launch_bounds__(WM * WN * 32, MINB)
 gemm_dmma_tmap_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB)

@@ -228,6 +228,9 @@ leaf_potrf_trtri_kernel(double* __restrict__ A, int lda, long long sA,
 // Same outputs / info convention as the v1 kernel (which it replaced: 233 us -> see profiles/).
 // ---------------------------------------------------------------------------------------
 #define LF_LD 132
+// optional phase clock stamps of CTA 0 (diagnostics: gpmpc_profile_leaf)
+__device__ long long* d_leaf_prof = nullptr;
+#define LEAF_STAMP(k) do { if (d_leaf_prof && blockIdx.x == 0 && threadIdx.x == 0) d_leaf_prof[k] = clock64(); } while (0)
 #define LF_NB 16
 #define LF_XLD 20
 #define LF_SMEM_DOUBLES (LEAF_N * LF_LD + 8 * 16 * 17 + 2 * LEAF_N * LF_XLD)
@@ -289,11 +292,13 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     double* Ab = A + (long long)blockIdx.x * sA;
     double* Lb = Li + (long long)blockIdx.x * sLi;
+    LEAF_STAMP(0);
     for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
         const int r = idx >> 7, c = idx & 127;
         S[r * LF_LD + c] = Ab[(long long)r * lda + c];
     }
     __syncthreads();
+    LEAF_STAMP(1);
 
     // ---------------- Cholesky, right-looking, nb = 16, with look-ahead ----------------
     // After the panel of step kb only the next block column is updated by everyone (C1); then warp 0
@@ -335,6 +340,7 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
     __syncthreads();
     panel(0, DinvAll);
     __syncthreads();
+    LEAF_STAMP(2);
     for (int kb = 0; kb < 7; ++kb) {
         const int c0 = kb * LF_NB, b0 = c0 + LF_NB;
         const int nt8 = (LEAF_N - b0) >> 3;
@@ -361,12 +367,14 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
         __syncthreads();
         panel(b0, DinvAll + (kb + 1) * 16 * 17);
         __syncthreads();
+        LEAF_STAMP(3 + kb);
     }
     for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
         const int r = idx >> 7, c = idx & 127;
         Ab[(long long)r * lda + c] = (c <= r) ? S[r * LF_LD + c] : 0.0;
     }
     __syncthreads();
+    LEAF_STAMP(10);
 
     // ---------------- triangular inverse by recursive doubling ----------------
     // the 16x16 diagonal inverses are known; for s = 16, 32, 64 every aligned pair of inverted
@@ -406,11 +414,13 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
             xp[0] = a0; xp[1] = a1;
         }
         __syncthreads();
+        LEAF_STAMP(sz == 16 ? 11 : (sz == 32 ? 12 : 13));
     }
     for (int idx = tid; idx < LEAF_N * LEAF_N; idx += 256) {
         const int r = idx >> 7, c = idx & 127;
         Lb[(long long)r * ldi + c] = (c <= r) ? S[r * LF_LD + c] : 0.0;
     }
+    LEAF_STAMP(14);
 }
 
 // batched 2-D copy  dst[b][r][c] = src[b][r][c]   (cols multiple of 2, 16-byte aligned)
@@ -940,4 +950,171 @@ append_row_kernel(double* __restrict__ L, double* __restrict__ Li, int ld, long 
     double* Lir = Li + (long long)a * sL + (long long)N * ld;
     for (int j = tid; j < N; j += 256) { Lr[j] = lv[j]; Lir[j] = -rv[j] * il; }
     if (tid == 0) { Lr[N] = lam; Lir[N] = il; }
+}
+
+// ---------------------------------------------------------------------------------------
+// First derivatives of the prediction w.r.t. the test input z (what CasADi's
+// AD produces for the MPC's NLP from the symbolic build_gp / build_TA_cov graphs,
+// gp_functions.py:111-173; mpc_class.py:390-412 differentiates them inside nlpsol):
+//   d ks_i / d z_d = ks_i (X_id - z_d)/ell_d^2
+//   d var / d z_d  = -2 sum_i beta_i ks_i (X_id - z_d)/ell_d^2 ,  beta = K^-1 ks = L^-T (L^-1 ks)
+//   Hm_de = d^2 mean / dz_d dz_e = sum_i alpha_i ks_i s_id s_ie - delta_de mean/ell_d^2 ,
+//           s_id = (X_id - z_d)/ell_d^2
+// Stage 1 (this kernel): per (output, test point, 1024-point block) partial sums
+//   PDV[d] = sum_i beta_i ks_i s_id            PH[q(d<=e)] = sum_i alpha_i ks_i s_id s_ie
+// ks is read back from KST (written by ks_mean_jac_kernel), beta rows from the second product.
+// grid (Npad/1024, Hc, outputs), 256 threads.
+// ---------------------------------------------------------------------------------------
+#define GR_CHUNK 1024
+template <int NXP>
+__global__ void __launch_bounds__(256)
+grad_reduce_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
+                   const double* __restrict__ hyp, int hyp_ld,
+                   const double* __restrict__ alpha, long long sal,
+                   const double* __restrict__ Z,
+                   const double* __restrict__ KST, const double* __restrict__ BETA, int ldk, long long sK,
+                   double* __restrict__ PDV, double* __restrict__ PH, int nblk, int Hc)
+{
+    extern __shared__ double gsm[];                 // S[Nx][257], WA[256]
+    __shared__ double red[8][NXP];
+    __shared__ double zs[NXP], ie2[NXP];
+    const int a = blockIdx.z, h = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+    double* S = gsm; double* WA = gsm + Nx * 257;
+    const double* hp = hyp + (long long)a * hyp_ld;
+    if (tid < NXP) {
+        const double e = (tid < Nx) ? hp[tid] : 1.0;
+        zs[tid] = (tid < Nx) ? Z[(long long)h * Nx + tid] : 0.0;
+        ie2[tid] = 1.0 / (e * e);
+    }
+    __syncthreads();
+    const int npairs = Nx * (Nx + 1) / 2;
+    const double* ks = KST + (long long)a * sK + (long long)h * ldk;
+    const double* be = BETA + (long long)a * sK + (long long)h * ldk;
+    const double* al = alpha + (long long)a * sal;
+    double dv[NXP];
+#pragma unroll
+    for (int d = 0; d < NXP; ++d) dv[d] = 0.0;
+    double hacc[3] = {0.0, 0.0, 0.0};               // pairs tid, tid+256, tid+512 (NX_MAX = 32: 528 pairs)
+    for (int sub = 0; sub < GR_CHUNK / 256; ++sub) {
+        const int i = blk * GR_CHUNK + sub * 256 + tid;
+        double k = 0.0, wb = 0.0, wa = 0.0;
+        if (i < N) { k = ks[i]; wb = be[i] * k; wa = al[i] * k; }
+#pragma unroll
+        for (int d = 0; d < NXP; ++d) {
+            if (d < Nx) {
+                const double sd = (i < N) ? (XT[(long long)d * ldx + i] - zs[d]) * ie2[d] : 0.0;
+                S[d * 257 + tid] = sd;
+                dv[d] = fma(wb, sd, dv[d]);
+            }
+        }
+        WA[tid] = wa;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int q = tid + 256 * r;
+            if (q < npairs) {
+                // q -> (d <= e), row-major upper packing: q = d*Nx - d(d-1)/2 + (e - d)
+                int d = 0, base = 0;
+                while (base + (Nx - d) <= q) { base += Nx - d; ++d; }
+                const int e = d + (q - base);
+                const double* sd = S + d * 257; const double* se = S + e * 257;
+                double acc = 0.0;
+                for (int t = 0; t < 256; ++t) acc = fma(WA[t] * sd[t], se[t], acc);
+                hacc[r] += acc;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int d = 0; d < NXP; ++d) dv[d] = warp_sum(dv[d]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < NXP; ++d) red[tid >> 5][d] = dv[d];
+    }
+    __syncthreads();
+    const long long rec = ((long long)a * Hc + h) * nblk + blk;
+    if (tid < Nx) {
+        double sacc = 0.0;
+        for (int w = 0; w < 8; ++w) sacc += red[w][tid];
+        PDV[rec * Nx + tid] = sacc;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int q = tid + 256 * r;
+        if (q < npairs) PH[rec * npairs + q] = hacc[r];
+    }
+}
+
+// Stage 2: per (test point h of the chunk, output a): dvar_dz (Nx) and the mean Hessian (Nx,Nx)
+// from the block partials; grid (Hc, outputs), 128 threads.  mean comes from the gather record.
+__global__ void __launch_bounds__(128)
+grad_finalize_kernel(const double* __restrict__ PDV, const double* __restrict__ PH, int nblk, int Hc,
+                     const double* __restrict__ hyp, int hyp_ld, int Nx, int Ny,
+                     const double* __restrict__ G, int Htot, int h0,
+                     double* __restrict__ dvar, double* __restrict__ hess)
+{
+    const int h = blockIdx.x, a = blockIdx.y, tid = threadIdx.x;
+    const int npairs = Nx * (Nx + 1) / 2;
+    const long long rec = ((long long)a * Hc + h) * nblk;
+    const double* hp = hyp + (long long)a * hyp_ld;
+    const double mean = G[(((long long)a) * Htot + h0 + h) * (Nx + 2)];
+    for (int d = tid; d < Nx; d += 128) {
+        double sacc = 0.0;
+        for (int b = 0; b < nblk; ++b) sacc += PDV[(rec + b) * Nx + d];
+        dvar[(((long long)(h0 + h)) * Ny + a) * Nx + d] = -2.0 * sacc;
+    }
+    for (int q = tid; q < npairs; q += 128) {
+        int d = 0, base = 0;
+        while (base + (Nx - d) <= q) { base += Nx - d; ++d; }
+        const int e = d + (q - base);
+        double sacc = 0.0;
+        for (int b = 0; b < nblk; ++b) sacc += PH[(rec + b) * npairs + q];
+        if (d == e) sacc -= mean / (hp[d] * hp[d]);
+        double* Hm = hess + (((long long)(h0 + h)) * Ny + a) * Nx * Nx;
+        Hm[d * Nx + e] = sacc;
+        Hm[e * Nx + d] = sacc;
+    }
+}
+
+// Stage 3: d cov[a][b] / d z_e for every test point (grid H, 128 threads):
+//   'ME': delta_ab dvar_a[e]
+//   'TA': delta_ab dvar_a[e] + sum_d Hm_a[d][e] (Sigma J_b)[d] + sum_d (J_a Sigma)[d] Hm_b[d][e]
+//   (derivative of diag(var) + J Sigma J^T, gp_functions.py:167-171; Sigma need not be symmetric)
+__global__ void __launch_bounds__(128)
+grad_cov_kernel(int Ny, int Nx, int method_ta, const double* __restrict__ Sigma, int sigma_per_point,
+                const double* __restrict__ J, const double* __restrict__ dvar, const double* __restrict__ hess,
+                double* __restrict__ dcov)
+{
+    extern __shared__ double sh[];                  // SJ[Ny][Nx] = Sigma J_b, JS[Ny][Nx] = J_a Sigma
+    double* SJ = sh; double* JS = sh + Ny * Nx;
+    const int h = blockIdx.x, tid = threadIdx.x;
+    const double* Jh = J + (long long)h * Ny * Nx;
+    if (method_ta) {
+        const double* Sg = Sigma + (sigma_per_point ? (long long)h * Nx * Nx : 0);
+        for (int idx = tid; idx < Ny * Nx; idx += 128) {
+            const int a = idx / Nx, d = idx % Nx;
+            double s1 = 0.0, s2 = 0.0;
+            for (int e = 0; e < Nx; ++e) {
+                s1 = fma(Sg[d * Nx + e], Jh[a * Nx + e], s1);          // (Sigma J_a)[d]
+                s2 = fma(Jh[a * Nx + e], Sg[e * Nx + d], s2);          // (J_a Sigma)[d]
+            }
+            SJ[idx] = s1; JS[idx] = s2;
+        }
+    }
+    __syncthreads();
+    const double* dv = dvar + (long long)h * Ny * Nx;
+    const double* Hh = hess + (long long)h * Ny * Nx * Nx;
+    double* out = dcov + (long long)h * Ny * Ny * Nx;
+    for (int idx = tid; idx < Ny * Ny * Nx; idx += 128) {
+        const int e = idx % Nx, b = (idx / Nx) % Ny, a = idx / (Nx * Ny);
+        double s = (a == b) ? dv[a * Nx + e] : 0.0;
+        if (method_ta) {
+            const double* Ha = Hh + (long long)a * Nx * Nx; const double* Hb = Hh + (long long)b * Nx * Nx;
+            for (int d = 0; d < Nx; ++d) {
+                s = fma(Ha[d * Nx + e], SJ[b * Nx + d], s);
+                s = fma(JS[a * Nx + d], Hb[d * Nx + e], s);
+            }
+        }
+        out[idx] = s;
+    }
 }

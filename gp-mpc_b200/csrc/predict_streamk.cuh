@@ -52,6 +52,7 @@ struct AssembleArgs {
 
 struct PredictParams {
     int nloc, nt, Hc;                 // local outputs, 128-column tiles per output, valid rows of this chunk
+    int upper;                        // 0: B lower triangular (k <= j, v = Linv ks); 1: B upper (k >= j, beta = Linv^T v)
     long long T, G;                   // k-steps per output = 4 nt (nt+1), total = nloc * T
     double* part;                     // [grid][2][BM*128] parked partial accumulators (fragment-major)
     unsigned int* tile_cnt;           // [nloc*nt]
@@ -65,6 +66,7 @@ struct PredictParams {
     double* Gloc; int slot0, Htot, h0;
     PeerArgs pa; int use_peers, publish;
     AssembleArgs as; int do_assemble;
+    unsigned long long* dbg;          // optional [grid][2]: globaltimer at CTA start / end (load-balance diagnostics)
 };
 
 // ---- stage 5: assemble mean (H,Ny), var (H,Ny), J (H,Ny,Nx) and the covariance for test point h:
@@ -263,6 +265,7 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
+    uint64_t* empty = full + STAGES;
     __shared__ double red[8][64];
     __shared__ unsigned int s_flag;
     __shared__ int s_ok;
@@ -272,33 +275,47 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
     const long long g0 = p.G * c / C;
     const int nsteps = (int)(p.G * (c + 1) / C - g0);           // this CTA's share of the k-step list
     if (nsteps <= 0) return;
+    if (p.dbg && threadIdx.x == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); p.dbg[2 * blockIdx.x] = t0; }
 
     // producer state lives in shared memory: only thread 0 touches it, so it costs no registers
     __shared__ PskIter s_pit;
     __shared__ int s_pg;
+    __shared__ uint64_t s_pol[2];
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, PSK_THREADS / 32); }
         mbar_fence_init();
     }
     __syncthreads();
 
+    // Pipeline without CTA-wide barriers: stage s is FULL when its two TMA boxes have landed and EMPTY
+    // when all 8 warps have read it.  Thread 0 refills two steps ahead: the stage it overwrites at
+    // step i was last read at step i-2, so its empty-wait is almost never a real wait and the warps
+    // may drift up to a step apart instead of meeting at a __syncthreads every 16 k.
     auto issue = [&]() {               // thread 0: TMA loads of step s_pg into stage s_pg % STAGES
         PskIter it = s_pit;
-        const int s = s_pg % STAGES;
+        const int pg = s_pg, s = pg % STAGES;
+        if (pg >= STAGES) mbar_wait(empty + s, (uint32_t)(((pg / STAGES) - 1) & 1));
         mbar_arrive_expect_tx(full + s, STAGE_TX);
-        tma_tile_g2s_3d(As + s * A_STAGE, &tmA, it.s * BK, 0, it.a, full + s);
-        tma_tile_g2s_3d(Bs + s * B_STAGE, &tmB, it.s * BK, it.jt * BN, it.a, full + s);
+        // lower: tile jt covers k in [0, (jt+1) 128); upper: the list position jt stands for column tile
+        // nt-1-jt, which covers k in [(nt-1-jt) 128, Npad) -- the same (jt+1)*8 steps
+        const int jta = p.upper ? p.nt - 1 - it.jt : it.jt;
+        const int k0 = (p.upper ? jta * BN : 0) + it.s * BK;
+        // ks^T (A) is re-read by every column tile: keep it in L2; L^-1 (B) is streamed exactly once
+        tma_tile_g2s_3d_hint(As + s * A_STAGE, &tmA, k0, 0, it.a, full + s, s_pol[1]);
+        tma_tile_g2s_3d_hint(Bs + s * B_STAGE, &tmB, k0, jta * BN, it.a, full + s, s_pol[0]);
         psk_iter_next(it, p.nt);
         s_pit = it;
-        s_pg = s_pg + 1;
+        s_pg = pg + 1;
     };
+    constexpr int AHEAD = 2;           // prefetch distance in steps
     if (tid == 0) {
         PskIter it;
         psk_iter_init(it, g0, p.T);
         s_pit = it; s_pg = 0;
+        s_pol[0] = l2_policy_evict_first(); s_pol[1] = l2_policy_evict_last();
 #pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s)
+        for (int s = 0; s < AHEAD; ++s)
             if (s_pg < nsteps) issue();
     }
 
@@ -317,9 +334,8 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
 
         for (int q = 0; q < seg; ++q, ++i) {
             const int s = i % STAGES;
+            if (tid == 0 && i + AHEAD < nsteps) issue();  // s_pg == i + AHEAD
             mbar_wait(full + s, (uint32_t)((i / STAGES) & 1));
-            __syncthreads();                              // everyone is done with the stage refilled below
-            if (tid == 0 && s_pg < nsteps) issue();
             const double* as = As + s * A_STAGE + g * 16 + kpar;
             const double* bs = Bs + s * B_STAGE + (warp * WTN + g) * 16 + kpar;
 #pragma unroll
@@ -335,6 +351,8 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
 #pragma unroll
                     for (int ni = 0; ni < NF; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);        // this warp is done reading stage s
         }
         cit.s = s_begin + seg - 1;
         psk_iter_next(cit, p.nt);
@@ -388,7 +406,7 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
             for (int mi = 0; mi < MF; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < NF; ++ni) {
-                    const int row = mi * 8 + g, col = jt * BN + warp * WTN + ni * 8 + 2 * t;
+                    const int row = mi * 8 + g, col = (p.upper ? p.nt - 1 - jt : jt) * BN + warp * WTN + ni * 8 + 2 * t;
                     *reinterpret_cast<double2*>(p.Vout + (long long)a * p.sV + (long long)row * p.ldv + col) =
                         make_double2(acc[mi][ni][0], acc[mi][ni][1]);
                 }
@@ -426,4 +444,5 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
         if (p.finalize) psk_finalize_output(p, a, warp, PSK_THREADS / 32, lane);
         psk_step_tail(p, smem, tid, PSK_THREADS, &s_flag, &s_ok);
     }
+    if (p.dbg && threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); p.dbg[2 * blockIdx.x + 1] = t1; }
 }

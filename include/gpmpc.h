@@ -121,6 +121,22 @@ int gpmpc_append(gpmpc_handle_t h, const double* x_new, const double* y_new);
  * GP.covar, gp_class.py:353-381. */
 int gpmpc_posterior_cov(gpmpc_handle_t h, int H, const double* Z, double* out);
 
+/* Prediction plus its first derivatives w.r.t. the test inputs -- what CasADi's AD extracts from
+ * the symbolic build_gp / build_TA_cov graphs (gp_functions.py:111-173) when nlpsol differentiates
+ * the MPC's NLP (mpc_class.py:390-412, :496-513).  Same arguments and outputs as gpmpc_predict
+ * (methods ME and TA; jac = d mean / d z), plus, each optional (NULL to skip):
+ *   dvar_dz (H,Ny,Nx)     d var_a / d z_e    = -2 (K^-1 ks)^T d ks/d z_e   (one extra L^-T product)
+ *   dcov_dz (H,Ny,Ny,Nx)  d cov[a][b] / d z_e of diag(var) + J Sigma J^T  (needs the mean Hessian)
+ *   hess    (H,Ny,Nx,Nx)  d^2 mean_a / d z_d d z_e
+ * d cov[a][b] / d Sigma[d][e] = J_a[d] J_b[e] ('TA') is formed by the caller from jac.
+ * The handle must own all outputs (single process, or a replicated handle). */
+int gpmpc_predict_grad(gpmpc_handle_t h, int method, int H, const double* Z, const double* Sigma,
+                       int sigma_per_point, double* mean, double* var, double* cov, double* jac,
+                       double* dvar_dz, double* dcov_dz, double* hess);
+
+/* Problem sizes of a handle (GP.get_size, gp_class.py:266-274: N, and Nx, Ny). */
+int gpmpc_get_size(gpmpc_handle_t h, int* N, int* Nx, int* Ny);
+
 /* Same with DEVICE pointers, enqueued on the handle's stream; returns without
  * synchronising unless sync != 0. */
 int gpmpc_predict_device(gpmpc_handle_t h, int method, int H, const double* dZ, const double* dSigma,
@@ -131,7 +147,9 @@ int gpmpc_predict_device(gpmpc_handle_t h, int method, int H, const double* dZ, 
 int gpmpc_get(gpmpc_handle_t h, int what, int a, double* dst);
 
 /* Engine options: "refine" (0/1: one step of iterative refinement of v = L\ks through
- * the stored factor), "ksplit" (split-K chunk of the predict product, 0 = auto). */
+ * the stored factor), "predict_ctas" (persistent grid of the stream-K predict product,
+ * 0 = two CTAs per SM), "peer" (0/1), "peer_timeout_s" (consumer wait for a peer's flag),
+ * "overlap", "gemm_variant", "leaf_variant", "small_tiles" (factorisation A/B switches). */
 int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value);
 
 /* Multi-GPU: one process per GPU.  Rank 0 calls gpmpc_comm_unique_id and ships the
@@ -157,6 +175,14 @@ int gpmpc_synchronize(gpmpc_handle_t h);
  * after one warm-up, average milliseconds in ms_out[0]; n = problem size override
  * (0 = the handle's N).  flops/bytes are derived by the caller. */
 int gpmpc_profile(gpmpc_handle_t h, int what, int n, int reps, double* ms_out);
+
+/* Load balance of the persistent predict product for an H-point batch: per-CTA busy time
+ * out4 = {shortest, longest, mean, first start -> last end} in microseconds (%globaltimer). */
+int gpmpc_profile_balance(gpmpc_handle_t h, int H, double* out4);
+
+/* Phase clock stamps (SM cycles since kernel start) of one 128x128 potrf+trtri leaf: out15 =
+ * {start, block loaded, first panel, block steps 1..7, L stored, inverse levels 16/32/64, L^-1 stored}. */
+int gpmpc_profile_leaf(gpmpc_handle_t h, double* out15);
 
 #ifdef __cplusplus
 }

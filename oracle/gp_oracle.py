@@ -579,6 +579,43 @@ def train_gp(X, Y, options=None):
 
 
 # ----------------------------------------------------------------------------
+# first derivatives w.r.t. the test input: checker for gpmpc_predict_grad
+# ----------------------------------------------------------------------------
+def predict_grad_fd(X, hyper, alpha, chol, Z, Sigma, method='TA', rel=1e-4):
+    """Central differences of the restated prediction (``gp_mean_var`` / ``gp_mean_jac`` /
+    ``ta_cov``, i.e. ``gp_functions.py:111-173``) w.r.t. every test-input coordinate: what
+    CasADi's AD computes for the MPC's NLP (``mpc_class.py:390-412``, ``:496-513``).  Oracle for
+    the analytic derivative kernels of the GPU engine (the reference has no closed forms).
+    Z:(H,Nx), Sigma:(Nx,Nx)|(H,Nx,Nx).  Returns dict(dmean (H,Ny,Nx), dvar (H,Ny,Nx),
+    dcov (H,Ny,Ny,Nx), hess (H,Ny,Nx,Nx))."""
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+    hyper = np.atleast_2d(np.asarray(hyper, dtype=np.float64))
+    H, Nx = Z.shape
+    Ny = hyper.shape[0]
+
+    def f(Zp):
+        m, v = gp_mean_var(X, hyper, alpha, chol, Zp)
+        J = gp_mean_jac(X, hyper, alpha, Zp)
+        c = ta_cov(v, J, Sigma) if method == 'TA' else me_cov(v)
+        return m, v, c, J
+
+    out = dict(dmean=np.zeros((H, Ny, Nx)), dvar=np.zeros((H, Ny, Nx)), dcov=np.zeros((H, Ny, Ny, Nx)),
+               hess=np.zeros((H, Ny, Nx, Nx)))
+    for e in range(Nx):
+        h = rel * np.maximum(1.0, np.abs(Z[:, e]))
+        Zp = Z.copy(); Zp[:, e] += h
+        Zm = Z.copy(); Zm[:, e] -= h
+        mp, vp, cp, Jp = f(Zp)
+        mm, vm, cm, Jm = f(Zm)
+        out['dmean'][:, :, e] = (mp - mm) / (2 * h[:, None])
+        out['dvar'][:, :, e] = (vp - vm) / (2 * h[:, None])
+        out['dcov'][:, :, :, e] = (cp - cm) / (2 * h[:, None, None])
+        out['hess'][:, :, :, e] = (Jp - Jm) / (2 * h[:, None, None])
+    return out
+
+
+# ----------------------------------------------------------------------------
 # fixtures / synthetic workloads shared by tests and bench
 # ----------------------------------------------------------------------------
 def synthetic_problem(N, Nx, Ny, config_id=0, H=30):

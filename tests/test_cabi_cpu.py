@@ -23,6 +23,10 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     hdr = open(os.path.join(ROOT, 'include', 'gpmpc.h')).read()
     declared = set(re.findall(r'\b(gpmpc_[A-Za-z_0-9]+)\s*\(', hdr))
+    # the CasADi `external` family (function + Jacobian function) of include/gpmpc_casadi.h
+    hdr2 = open(os.path.join(ROOT, 'include', 'gpmpc_casadi.h')).read().split('#ifndef GPMPC_CASADI_H')[1]
+    declared |= set(re.findall(r'\b((?:jac_)?gp_b200[A-Za-z_0-9]*)\s*\(', hdr2))
+    assert {'gp_b200', 'jac_gp_b200', 'gp_b200_bind', 'gp_b200_sparsity_out', 'jac_gp_b200_work'} <= declared
     bound = {s[0] for s in L.SYMBOLS}
     assert declared == bound, (declared ^ bound)
     for name in declared:
@@ -89,3 +93,16 @@ def test_bench_workload_generator_matches_the_oracle_generator():
     for k in ('X', 'Y', 'hyper', 'Z', 'Sigma'):
         assert np.array_equal(a[k], b[k])
     assert set(bench.WORKLOADS) == {'c2', 'c3', 'c5'}
+
+
+def test_casadi_external_metadata_without_a_gpu():
+    """The `casadi.external` helper functions answer without a device; patterns exist only once bound."""
+    lib = _lib().load()
+    assert lib.gp_b200_n_in() == 2 and lib.gp_b200_n_out() == 2
+    assert lib.jac_gp_b200_n_in() == 4 and lib.jac_gp_b200_n_out() == 4
+    assert [lib.gp_b200_name_in(i) for i in range(2)] == [b'z', b'sigma']
+    assert [lib.jac_gp_b200_name_out(i) for i in range(4)] == [b'jac_mean_z', b'jac_mean_sigma', b'jac_cov_z', b'jac_cov_sigma']
+    assert not lib.gp_b200_sparsity_in(0) and not lib.jac_gp_b200_sparsity_out(2)      # not bound
+    sz = [ctypes.c_longlong(-1) for _ in range(4)]
+    assert lib.gp_b200_work(*[ctypes.byref(x) for x in sz]) == 0 and [x.value for x in sz] == [2, 2, 0, 0]
+    assert lib.gp_b200_bind(None, 1, 5) != 0

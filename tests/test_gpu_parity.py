@@ -293,6 +293,120 @@ def test_c5_full_size_vs_independent_cholesky():
     eng.close()
 
 
+# ------------------------------------------------------------------ derivatives for the CasADi adapter (8f row 1)
+@pytest.mark.parametrize('case', ['tank', 'car', 'syn700', 'syn1500'])
+def test_predict_grad_vs_central_differences(case):
+    """gpmpc_predict_grad: d var / d z, d cov / d z (ME and TA) and the mean Hessian against central
+    differences of the oracle prediction (<= 1e-5, the FD truncation/rounding level); the values
+    themselves must equal gpmpc_predict's bit for bit."""
+    if case in ('tank', 'car'):
+        m = load_fixture(case); X, Y, hyper = m['X'], m['Y'], m['hyper']
+        rng = np.random.default_rng(5)
+        Z = X[rng.choice(X.shape[0], 6, replace=False)] + 0.05 * rng.standard_normal((6, X.shape[1]))
+        A = rng.standard_normal((X.shape[1],) * 2); Sigma = 1e-3 * np.eye(X.shape[1]) + 1e-4 * A @ A.T
+    else:
+        n = int(case[3:]); p = orc.synthetic_problem(n, 7 if n == 700 else 17, 3, config_id=n, H=9 if n == 700 else 66)
+        X, Y, hyper, Z, Sigma = p['X'], p['Y'], p['hyper'], p['Z'], p['Sigma']
+    Ny, Nx = Y.shape[1], X.shape[1]
+    eng, _ = _fit_engine(X, Y, hyper)
+    L = _L()
+    post = orc.postfit(X, Y, hyper, lapack_general_solve=False)
+    Sg = np.stack([Sigma * (1 + 0.05 * h) for h in range(Z.shape[0])])
+    for method, name, S in ((L.METHOD_TA, 'TA', Sg), (L.METHOD_ME, 'ME', None)):
+        g = eng.predict_grad(Z, S, method, want_hess=True)
+        mean, var, cov, jac = eng.predict(Z, S, method)
+        assert np.array_equal(g['mean'], mean) and np.array_equal(g['var'], var)
+        assert np.array_equal(g['cov'], cov) and np.array_equal(g['jac'], jac)
+        fd = orc.predict_grad_fd(X, hyper, post['alpha'], post['chol'], Z, S, name)
+        tol = 1e-5 if case != 'car' else 3e-5        # car: cond(K) ~ 1e10 makes the FD of var itself noisy
+        assert relinf(g['jac'], fd['dmean']) < tol
+        assert relinf(g['hess'], fd['hess']) < tol
+        assert relinf(g['dvar_dz'], fd['dvar']) < tol
+        assert relinf(g['dcov_dz'], fd['dcov']) < tol
+        assert np.array_equal(g['hess'], np.swapaxes(g['hess'], 2, 3))
+    eng.close()
+
+
+def test_casadi_external_entry_points():
+    """The `casadi.external`-shaped C entry points (include/gpmpc_casadi.h) driven through ctypes the
+    way CasADi's importer drives them: sizes / sparsity patterns, gp_b200 == gpmpc_predict over all
+    shooting nodes, jac_gp_b200's block-diagonal CCS nonzeros == gpmpc_predict_grad."""
+    import ctypes as C
+    m = load_fixture('tank'); X, Y, hyper = m['X'], m['Y'], m['hyper']
+    Ny, Nx, Nt = 4, 6, 5
+    eng, _ = _fit_engine(X, Y, hyper)
+    Lb = _L(); lib = Lb.load()
+    rng = np.random.default_rng(8)
+    Z = X[:Nt] + 0.1 * rng.standard_normal((Nt, Nx))
+    Sg = np.stack([1e-3 * np.eye(Nx) + 1e-4 * (lambda A: A @ A.T)(rng.standard_normal((Nx, Nx))) for _ in range(Nt)])
+    assert lib.gp_b200_bind(eng.h, Lb.METHOD_TA, Nt) == 0
+    assert lib.gp_b200_n_in() == 2 and lib.gp_b200_n_out() == 2
+    assert lib.jac_gp_b200_n_in() == 4 and lib.jac_gp_b200_n_out() == 4
+    assert lib.gp_b200_name_in(0) == b'z' and lib.gp_b200_name_out(1) == b'cov'
+    assert [lib.gp_b200_sparsity_in(0)[k] for k in range(3)] == [Nx, Nt, 1]
+    assert [lib.gp_b200_sparsity_in(1)[k] for k in range(3)] == [Nx, Nx * Nt, 1]
+    assert [lib.gp_b200_sparsity_out(0)[k] for k in range(3)] == [Ny, Nt, 1]
+    assert [lib.gp_b200_sparsity_out(1)[k] for k in range(3)] == [Ny, Ny * Nt, 1]
+    dp = C.POINTER(C.c_double)
+
+    def call(fn, ins, outs):
+        arg = (dp * len(ins))(*[a.ctypes.data_as(dp) for a in ins])
+        res = (dp * len(outs))(*[a.ctypes.data_as(dp) for a in outs])
+        assert fn(arg, res, None, None, 0) == 0
+
+    # column-major dense: z (Nx x Nt) is (Nt,Nx) row-major; sigma (Nx x Nx*Nt): block t column-major
+    z_cm = np.ascontiguousarray(Z)
+    s_cm = np.ascontiguousarray(np.transpose(Sg, (0, 2, 1)))
+    mean_cm = np.empty((Nt, Ny)); cov_cm = np.empty((Nt, Ny, Ny))
+    call(lib.gp_b200, [z_cm, s_cm], [mean_cm, cov_cm])
+    mean, var, cov, jac = eng.predict(Z, Sg, Lb.METHOD_TA)
+    assert np.array_equal(mean_cm, mean) and np.array_equal(cov_cm, np.transpose(cov, (0, 2, 1)))
+    g = eng.predict_grad(Z, Sg, Lb.METHOD_TA)
+
+    def ccs(ptr):
+        nrow, ncol = ptr[0], ptr[1]
+        colind = [ptr[2 + k] for k in range(ncol + 1)]
+        rows = [ptr[2 + ncol + 1 + k] for k in range(colind[-1])]
+        return nrow, ncol, colind, rows
+
+    pats = [ccs(lib.jac_gp_b200_sparsity_out(k)) for k in range(4)]
+    assert (pats[0][0], pats[0][1], pats[0][2][-1]) == (Ny * Nt, Nx * Nt, Nt * Ny * Nx)
+    assert (pats[1][0], pats[1][1], pats[1][2][-1]) == (Ny * Nt, Nx * Nx * Nt, 0)
+    assert (pats[2][0], pats[2][1], pats[2][2][-1]) == (Ny * Ny * Nt, Nx * Nt, Nt * Ny * Ny * Nx)
+    assert (pats[3][0], pats[3][1], pats[3][2][-1]) == (Ny * Ny * Nt, Nx * Nx * Nt, Nt * Ny * Ny * Nx * Nx)
+    outs = [np.zeros(max(1, pt[2][-1])) for pt in pats]
+    call(lib.jac_gp_b200, [z_cm, s_cm, mean_cm, cov_cm], outs)
+
+    def dense(pat, vals):
+        nrow, ncol, colind, rows = pat
+        D = np.zeros((nrow, ncol))
+        for c in range(ncol):
+            for k in range(colind[c], colind[c + 1]):
+                D[rows[k], c] = vals[k]
+        return D
+
+    Jm = dense(pats[0], outs[0]); Jc = dense(pats[2], outs[2]); Js = dense(pats[3], outs[3])
+    for t in range(Nt):
+        assert np.array_equal(Jm[t * Ny:(t + 1) * Ny, t * Nx:(t + 1) * Nx], g['jac'][t])
+        blk = Jc[t * Ny * Ny:(t + 1) * Ny * Ny, t * Nx:(t + 1) * Nx]         # rows a + Ny*b
+        assert np.array_equal(blk.reshape(Ny, Ny, Nx).transpose(1, 0, 2), g['dcov_dz'][t])
+        sb = Js[t * Ny * Ny:(t + 1) * Ny * Ny, t * Nx * Nx:(t + 1) * Nx * Nx]  # cols d + Nx*e
+        want = np.einsum('ad,be->baed', g['jac'][t], g['jac'][t]).reshape(Ny * Ny, Nx * Nx)
+        assert np.array_equal(sb, want)
+    Jm[:, :] = np.where(np.kron(np.eye(Nt), np.ones((Ny, Nx))) > 0, 0.0, Jm)
+    assert not Jm.any()                                                       # nothing off the block diagonal
+    # d cov / d Sigma against a finite difference of the restated TA covariance (linear in Sigma)
+    post = orc.postfit(X, Y, hyper, lapack_general_solve=False)
+    mo, vo = orc.gp_mean_var(X, hyper, post['alpha'], post['chol'], Z[:1])
+    Jo = orc.gp_mean_jac(X, hyper, post['alpha'], Z[:1])
+    E = np.zeros((Nx, Nx)); E[1, 3] = 1.0
+    dS = (orc.ta_cov(vo, Jo, Sg[0] + E) - orc.ta_cov(vo, Jo, Sg[0]))[0]
+    assert relinf(Js[:Ny * Ny, 1 + Nx * 3].reshape(Ny, Ny).T, dS) < 1e-6
+    lib.gp_b200_unbind()
+    assert not lib.gp_b200_sparsity_in(0)
+    eng.close()
+
+
 # ------------------------------------------------------------------ 'EM' exact moment matching (8f row 2)
 def test_exact_moment_matching_vs_restatement():
     """gp_exact_moment (gp_functions.py:344-418).  The EM covariance subtracts invK from

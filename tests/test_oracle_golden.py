@@ -185,3 +185,33 @@ def test_large_size_helpers_match_the_restatement():
         m = load_fixture(name)
         f = orc.factor_large(m['X'], m['Y'][:, 0], m['hyper'][0])
         assert relinf(f['chol'], m['chol'][0]) < (1e-10 if name == 'tank' else 2e-9)   # the reference's stored factor
+
+
+def test_fd_derivative_oracle_matches_closed_forms():
+    """predict_grad_fd (the checker of gpmpc_predict_grad) against the closed forms evaluated in
+    numpy on the tank fixture: d var/dz = -2 (K^-1 ks)^T d ks/dz, mean Hessian, d cov_TA/dz."""
+    from scipy.linalg import solve_triangular
+    m = load_fixture('tank'); X, Y, hyper = m['X'], m['Y'], m['hyper']
+    Ny, Nx = Y.shape[1], X.shape[1]
+    post = orc.postfit(X, Y, hyper, lapack_general_solve=False)
+    rng = np.random.default_rng(5)
+    Z = X[:3] + 0.05 * rng.standard_normal((3, Nx))
+    A = rng.standard_normal((Nx, Nx)); S = 1e-3 * np.eye(Nx) + 1e-4 * A @ A.T
+    fd = orc.predict_grad_fd(X, hyper, post['alpha'], post['chol'], Z, S, 'TA')
+    mean, var = orc.gp_mean_var(X, hyper, post['alpha'], post['chol'], Z)
+    J = orc.gp_mean_jac(X, hyper, post['alpha'], Z)
+    dvar = np.zeros((3, Ny, Nx)); Hm = np.zeros((3, Ny, Nx, Nx))
+    for a in range(Ny):
+        ell = hyper[a, :Nx]
+        ks = orc.covSEard(X, Z, ell, hyper[a, Nx] ** 2)
+        v = solve_triangular(post['chol'][a], ks, lower=True)
+        beta = solve_triangular(post['chol'][a], v, lower=True, trans='T')
+        for h in range(3):
+            s = (X - Z[h]) / ell ** 2
+            dvar[h, a] = -2 * (beta[:, h] * ks[:, h]) @ s
+            Hm[h, a] = (s * (post['alpha'][a] * ks[:, h])[:, None]).T @ s - np.diag(mean[h, a] / ell ** 2)
+    dcov = np.einsum('hade,hbd->habe', Hm, np.einsum('de,hbe->hbd', S, J)) + np.einsum('had,hbde->habe', J @ S, Hm)
+    for a in range(Ny):
+        dcov[:, a, a, :] += dvar[:, a, :]
+    assert relinf(J, fd['dmean']) < 1e-7 and relinf(Hm, fd['hess']) < 1e-6
+    assert relinf(dvar, fd['dvar']) < 1e-5 and relinf(dcov, fd['dcov']) < 1e-5
