@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get('GPMPC_LIB', os.path.join(_HERE, 'lib', 'libgpmpc.so')
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NCCL, ERR_NOTPD = 0, -1, -2, -3, -4, -5
 METHOD_ME, METHOD_TA, METHOD_EM = 0, 1, 2
-GET_CHOL, GET_ALPHA, GET_INVK, GET_K, GET_LOGDET, GET_LINV = range(6)
+GET_CHOL, GET_ALPHA, GET_INVK, GET_K, GET_LOGDET, GET_LINV, GET_ALPHA_NLML = range(7)
 PROF_KBUILD_FULL, PROF_KBUILD_LOWER, PROF_SYRK, PROF_FACTORIZE, PROF_TRIGEMM = range(5)
 
 # every symbol include/gpmpc.h declares: (name, restype, argtypes)
@@ -30,6 +30,7 @@ SYMBOLS = [
     ('gpmpc_last_error', C.c_char_p, [_H]),
     ('gpmpc_set_data', C.c_int, [_H, _dp, _dp]),
     ('gpmpc_set_hyper', C.c_int, [_H, _dp, C.c_int]),
+    ('gpmpc_set_y', C.c_int, [_H, C.c_int, _dp]),
     ('gpmpc_build_K', C.c_int, [_H, C.c_int, _dp]),
     ('gpmpc_factorize', C.c_int, [_H, C.c_double, _ip]),
     ('gpmpc_nlml', C.c_int, [_H, C.c_int, _dp, _dp, _dp]),
@@ -153,6 +154,10 @@ class Engine:
         assert hyper.ndim == 2 and hyper.shape[0] == self.Ny and hyper.shape[1] >= self.Nx + 2
         self._check(self.lib.gpmpc_set_hyper(self.h, _ptr(hyper), hyper.shape[1]))
 
+    def set_y(self, a, y):
+        y = _f64(y, (self.N,))
+        self._check(self.lib.gpmpc_set_y(self.h, int(a), _ptr(y)))
+
     def build_K(self, a):
         K = np.empty((self.N, self.N))
         self._check(self.lib.gpmpc_build_K(self.h, int(a), _ptr(K)))
@@ -179,7 +184,7 @@ class Engine:
     def get(self, what, a):
         N = self.N
         shape = {GET_CHOL: (N, N), GET_LINV: (N, N), GET_INVK: (N, N), GET_K: (N, N),
-                 GET_ALPHA: (N,), GET_LOGDET: (1,)}[what]
+                 GET_ALPHA: (N,), GET_ALPHA_NLML: (N,), GET_LOGDET: (1,)}[what]
         out = np.empty(shape)
         self._check(self.lib.gpmpc_get(self.h, int(what), int(a), _ptr(out)))
         return out

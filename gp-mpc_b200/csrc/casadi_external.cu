@@ -63,7 +63,7 @@ int eval(const casadi_real* Z, const casadi_real* Sigma, bool grad)
 {
     Bound& b = g_b;
     if (!b.h || !Z) return 1;
-    const int Nt = b.Nt, Nx = b.Nx, Ny = b.Ny;
+    const int Nt = b.Nt, Nx = b.Nx;
     const bool ta = b.method == GPMPC_METHOD_TA;
     if (ta) {
         if (!Sigma) return 1;
@@ -135,9 +135,14 @@ extern "C" int gp_b200(const casadi_real** arg, casadi_real** res, casadi_int* i
     if (!arg || !res) return 1;
     if (eval(arg[0], arg[1], false)) return 1;
     const Bound& b = g_b;
-    // (Nt,Ny) row-major == Ny x Nt column-major; cov blocks are symmetric
+    // (Nt,Ny) row-major == Ny x Nt column-major; each Ny x Ny block is written column-major
+    // (element (a,b) at a + Ny*b) -- the blocks are symmetric only up to rounding
     if (res[0]) std::copy(b.mean.begin(), b.mean.end(), res[0]);
-    if (res[1]) std::copy(b.cov.begin(), b.cov.end(), res[1]);
+    if (res[1])
+        for (int t = 0; t < b.Nt; ++t)
+            for (int bb = 0; bb < b.Ny; ++bb)
+                for (int a = 0; a < b.Ny; ++a)
+                    res[1][((size_t)t * b.Ny + bb) * b.Ny + a] = b.cov[((size_t)t * b.Ny + a) * b.Ny + bb];
     return 0;
 }
 

@@ -22,7 +22,7 @@
 #define GPMPC_VERSION 100
 #define HB 64                 // test points per predict pass (rows of the KS^T operand)
 #define NX_MAX 32
-#define PSK_MAX_CTAS 1024
+#define PSK_MAX_CTAS 2048
 #define MAX_DEPTH 12           // recursion depth bound: 128 * 2^12 rows
 
 // ------------------------------------------------------------------------------------
@@ -80,7 +80,7 @@ struct gpmpc_handle_s {
     // predict
     double *dKST = nullptr, *dPart = nullptr, *dPMJ = nullptr, *dSQ = nullptr, *dV = nullptr, *dR = nullptr, *dR2 = nullptr;
     unsigned int* dCnt = nullptr;     // stream-K counters: [nloc*nt tile | nloc output | 1 done], self-cleaning
-    int psk_ctas = 0, opt_predict_ctas = 0;   // persistent grid of the predict product (2 CTAs per SM)
+    int psk_ctas = 0, opt_predict_ctas = 0, partCtas = 0;   // persistent grid of the predict product (2 CTAs per SM)
     double *dCovV = nullptr, *dCovOut = nullptr; long long covVcap = 0, covOutcap = 0;   // GP.covar scratch pool
     // predict_grad: U = Linv^T per output (lazy), beta rows, partial sums, per-batch derivative slabs
     double *dUall = nullptr, *dBeta = nullptr, *dPDV = nullptr, *dPH = nullptr, *dGradOut = nullptr; bool u_valid = false; int gradHcap = 0;
@@ -295,13 +295,15 @@ static int launch_alpha(gpmpc_handle_t h, int a, int batch)
     trmv_lower_kernel<<<g1, 256, 0, h->st>>>(Li, n, slab(h), h->dY + (long long)a * n, n,
                                               h->dTmp + (long long)a * n, n, n);
     CUDA_TRY(cudaGetLastError());
-    dim3 g2(n / 32, 1, batch);
-    trmv_lower_T_kernel<<<g2, 256, 0, h->st>>>(Li, n, slab(h), h->dTmp + (long long)a * n, n,
-                                                h->dAlpha + (long long)a * n, n, n);
+    // alpha = Li^T tmp in row chunks (partials in the W1 workspace, free outside the recursion), then
+    // one pass that sums the partials, takes log det and y . alpha
+    const int nch = (n + TRT_ROWS - 1) / TRT_ROWS;
+    double* P = h->dW1 + (long long)a * wslab(h);
+    dim3 g2(n / 32, nch, batch);
+    trmv_lower_T_part_kernel<<<g2, 256, 0, h->st>>>(Li, n, slab(h), h->dTmp + (long long)a * n, n, P, wslab(h), n);
     CUDA_TRY(cudaGetLastError());
-    logdet_dot_kernel<<<batch, 256, 0, h->st>>>(h->dL + (long long)a * slab(h), n, slab(h),
-                                                 h->dY + (long long)a * n, n,
-                                                 h->dAlpha + (long long)a * n, n, n, h->dRes + 2 * a);
+    alpha_logdet_kernel<<<batch, 1024, 0, h->st>>>(P, wslab(h), nch, h->dL + (long long)a * slab(h), n, slab(h),
+                                                   h->dY + (long long)a * n, n, h->dAlpha + (long long)a * n, n, n, h->dRes + 2 * a);
     CUDA_TRY(cudaGetLastError());
     return GPMPC_OK;
 }
@@ -499,6 +501,23 @@ extern "C" int gpmpc_set_data(gpmpc_handle_t h, const double* X, const double* Y
     return GPMPC_OK;
 }
 
+static int local_index(gpmpc_handle_t h, int a);
+
+// Replace the target vector of global output a (N doubles): GP passes the residual y - m(X) when a
+// prior mean function is in use (alpha = K^-1 (y - m(X)), optimize.py:492-494).
+extern "C" int gpmpc_set_y(gpmpc_handle_t h, int a, const double* y)
+{
+    if (!h || !y) return GPMPC_ERR_ARG;
+    if (!h->has_data) { set_error(h, "gpmpc_set_y: set_data first"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int al = local_index(h, a);
+    if (al < 0) return GPMPC_ERR_ARG;
+    CUDA_TRY(cudaMemcpyAsync(h->dY + (long long)al * h->Npad, y, (size_t)h->N * 8, cudaMemcpyHostToDevice, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    h->factorized = false;
+    return GPMPC_OK;
+}
+
 extern "C" int gpmpc_set_hyper(gpmpc_handle_t h, const double* hyper, int ld)
 {
     if (!h || !hyper || ld < h->Nx + 2) { if (h) set_error(h, "gpmpc_set_hyper: ld < Nx+2"); return GPMPC_ERR_ARG; }
@@ -671,6 +690,11 @@ extern "C" int gpmpc_get(gpmpc_handle_t h, int what, int a, double* dst)
     const int al = local_index(h, a);
     if (al < 0) return GPMPC_ERR_ARG;
     if (what == GPMPC_GET_K) return gpmpc_build_K(h, a, dst);
+    if (what == GPMPC_GET_ALPHA_NLML) {       // alpha of the last gpmpc_nlml(a, theta) evaluation
+        CUDA_TRY(cudaMemcpyAsync(dst, h->dAlpha + (long long)al * h->Npad, h->N * 8, cudaMemcpyDeviceToHost, h->st));
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        return GPMPC_OK;
+    }
     if (!h->factorized) { set_error(h, "gpmpc_get: call gpmpc_factorize first"); return GPMPC_ERR_STATE; }
     switch (what) {
     case GPMPC_GET_CHOL: return extract_to_host(h, h->dL + (long long)al * slab(h), dst, 1);
@@ -722,10 +746,19 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
         h->psk_ctas = 2 * sms;
         const long long nt = np / 128;
         ALLOC(h->dKST, (long long)h->nloc * HB * np);
-        ALLOC(h->dPart, (long long)PSK_MAX_CTAS * 2 * HB * PSK_BN);
         ALLOC(h->dPMJ, (long long)h->nloc * HB * ((np + 1023) / 1024) * (h->Nx + 1));
         ALLOC(h->dSQ, (long long)h->nloc * HB * nt);
         ALLOC(h->dCnt, (long long)h->nloc * nt + h->nloc + 1);
+    }
+    {   // parked stream-K partials: two BM x 128 slots per persistent CTA
+        const int want = std::max(h->psk_ctas, h->opt_predict_ctas);
+        if (want > h->partCtas) {
+            CUDA_TRY(cudaStreamSynchronize(h->st));
+            if (h->dPart) cudaFree(h->dPart);
+            h->dPart = nullptr; h->partCtas = 0;
+            ALLOC(h->dPart, (long long)want * 2 * HB * PSK_BN);
+            h->partCtas = want;
+        }
     }
     if (h->opt_refine && !h->dR2) {
         if (!h->dV) { ALLOC(h->dV, (long long)h->nloc * HB * np); ALLOC(h->dR, (long long)h->nloc * HB * np); }

@@ -491,6 +491,68 @@ trmv_lower_T_kernel(const double* __restrict__ T, int ld, long long sT,
     }
 }
 
+// out = T^T * w in row chunks of TRT_ROWS: grid (n/32, ceil(n/TRT_ROWS), batch); block (k-block, c)
+// sums rows [c*TRT_ROWS, (c+1)*TRT_ROWS) of its 32 columns into P[batch][c][k].  Chunks entirely
+// above the diagonal are skipped; the consumer sums chunks c >= k/TRT_ROWS in ascending order
+// (deterministic).  The one-block-per-32-columns kernel above needs N/32 >= #SMs*4 to fill the GPU
+// (244 us at N=4096); this one has N^2/16384 blocks.
+#define TRT_ROWS 512
+__global__ void __launch_bounds__(256)
+trmv_lower_T_part_kernel(const double* __restrict__ T, int ld, long long sT,
+                         const double* __restrict__ w, long long sw,
+                         double* __restrict__ P, long long sP, int n)
+{
+    __shared__ double red[8][33];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int k0 = blockIdx.x * 32, c = blockIdx.y;
+    const int r1 = min(n, (c + 1) * TRT_ROWS);
+    if (r1 <= k0) return;
+    const int r0 = max(c * TRT_ROWS, k0);
+    const int k = k0 + lane;
+    const double* Tb = T + (long long)blockIdx.z * sT;
+    const double* ww = w + (long long)blockIdx.z * sw;
+    double s = 0.0;
+    for (int i = r0 + wp; i < r1; i += 8)
+        if (i >= k) s = fma(Tb[(long long)i * ld + k], ww[i], s);
+    red[wp][lane] = s;
+    __syncthreads();
+    if (wp == 0) {
+        double r = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r += red[q][lane];
+        P[(long long)blockIdx.z * sP + (long long)c * n + k] = r;
+    }
+}
+
+// alpha[k] = sum of the row-chunk partials; res[0] = 2 sum_i log L_ii (a4, optimize.py:352), res[1] = y . alpha
+__global__ void __launch_bounds__(1024)
+alpha_logdet_kernel(const double* __restrict__ P, long long sP, int nch,
+                    const double* __restrict__ L, int ld, long long sL,
+                    const double* __restrict__ y, long long sy,
+                    double* __restrict__ al, long long sal, int n, double* __restrict__ res)
+{
+    __shared__ double r0[32], r1[32];
+    const double* Lb = L + (long long)blockIdx.x * sL;
+    const double* Pb = P + (long long)blockIdx.x * sP;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        double a = 0.0;
+        for (int c = i / TRT_ROWS; c < nch; ++c) a += Pb[(long long)c * n + i];
+        al[(long long)blockIdx.x * sal + i] = a;
+        s0 += log(fabs(Lb[(long long)i * ld + i]));
+        s1 = fma(y[(long long)blockIdx.x * sy + i], a, s1);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = s0; r1[threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < 32; ++q) { a += r0[q]; b += r1[q]; }
+        res[2 * blockIdx.x] = 2.0 * a;
+        res[2 * blockIdx.x + 1] = b;
+    }
+}
+
 // per batch entry: res[0] = sum_i log(L_ii) * 2 (a4, optimize.py:352), res[1] = y . alpha
 __global__ void __launch_bounds__(256)
 logdet_dot_kernel(const double* __restrict__ L, int ld, long long sL,

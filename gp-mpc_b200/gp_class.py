@@ -24,6 +24,7 @@ import numpy as np
 
 from . import _lib
 from .comm import Comm
+from .mean_functions import mean_function, mean_jacobian
 from .optimize import train_gp_b200
 from .partition import choose_mode, output_block, point_block
 
@@ -40,12 +41,17 @@ class GP:
     def __init__(self, X, Y, mean_func="zero", gp_method="TA",
                  optimizer_opts=None, hyper=None, normalize=True, multistart=1,
                  xlb=None, xub=None, ulb=None, uub=None, meta=None,
-                 optimize_nummeric=True, device=None, comm=None, engine_factory=None):
+                 optimize_nummeric=True, device=None, comm=None, engine_factory=None,
+                 prior_mean_in_predict=False):
         """ Initialize and optimize GP model  (reference gp_class.py:21-75)
 
         Extra keyword arguments (not in the reference): ``device`` (CUDA ordinal,
         default $LOCAL_RANK or 0), ``comm`` (a ``Comm``; default: the initialised
-        torch.distributed world, else single process), ``engine_factory`` (tests).
+        torch.distributed world, else single process), ``engine_factory`` (tests),
+        ``prior_mean_in_predict``: the reference fits alpha on y - m(X) (optimize.py:492-494) but
+        never adds the prior mean m(z) back when predicting (build_gp is always called without
+        meanFunc, gp_class.py:69-71).  False (default) replicates that; True adds m(z)
+        to the predicted mean and d m/d z to the Jacobian / Taylor covariance.
         """
         X = np.array(X, dtype=np.float64).copy()
         Y = np.array(Y, dtype=np.float64).copy()
@@ -66,6 +72,7 @@ class GP:
         self.__engine_factory = engine_factory or _lib.Engine
         self.__engine = None
         self.__invK = None
+        self.__prior_mean_in_predict = bool(prior_mean_in_predict)
         self.__xlb = self.__xub = self.__ulb = self.__uub = None
 
         if meta is not None:                         # gp_class.py:42-50
@@ -145,7 +152,14 @@ class GP:
         if not all(c.allgather_object(ok)):
             eng.set_option('peer', 0)
 
+    def __has_prior_mean(self):
+        return self.__mean_func != 'zero' and self.__hyper.shape[1] > self.__Nx + 2
+
     def __factorize(self):
+        if self.__has_prior_mean():
+            # alpha = K^-1 (y - m(X))  (optimize.py:492-494): the engine factorises on the residual
+            for a in self.__engine.local_outputs:
+                self.__engine.set_y(a, self.__Y[:, a] - mean_function(self.__hyper[a], self.__X, self.__mean_func))
         self.__engine.set_hyper(self.__hyper)
         info = self.__engine.factorize(1e-8)
         for k, a in enumerate(self.__engine.local_outputs):
@@ -275,14 +289,36 @@ class GP:
         """Batched predict in the GP's standardised space.  Z:(H,Nx)."""
         Z = np.ascontiguousarray(Z, dtype=np.float64).reshape(-1, self.__Nx)
         c = self.__comm
+        add_pm = self.__prior_mean_in_predict and self.__has_prior_mean() and method != 'EM'
+        need_jac = want_jac or add_pm
         if c.world > 1 and self.__mode == 'points':
             b, n = point_block(Z.shape[0], c.rank, c.world)
             Sg = Sigma[b:b + n] if (Sigma is not None and np.ndim(Sigma) == 3) else Sigma
-            part = self.__engine.predict(Z[b:b + n], Sg, _GPU_METHODS[method], want_cov, want_jac) if n else None
+            part = self.__engine.predict(Z[b:b + n], Sg, _GPU_METHODS[method], want_cov, need_jac) if n else None
             parts = [p for p in c.allgather_object(part) if p is not None]
-            return tuple(None if parts[0][k] is None else np.concatenate([p[k] for p in parts], 0)
-                         for k in range(4))
-        return self.__engine.predict(Z, Sigma, _GPU_METHODS[method], want_cov, want_jac)
+            out = tuple(None if parts[0][k] is None else np.concatenate([p[k] for p in parts], 0)
+                        for k in range(4))
+        else:
+            out = self.__engine.predict(Z, Sigma, _GPU_METHODS[method], want_cov, need_jac)
+        if add_pm:
+            out = self.__add_prior_mean(Z, Sigma, method, out, want_cov, want_jac)
+        return out
+
+    def __add_prior_mean(self, Z, Sigma, method, out, want_cov, want_jac):
+        """flag-gated fix of SURVEY q2: mean += m(z), J += dm/dz, and for 'TA' the J Sigma J^T term is
+        rebuilt with the full Jacobian (O(H Ny Nx^2) host work)."""
+        mean, var, cov, jac = out
+        M = np.column_stack([mean_function(self.__hyper[a], Z, self.__mean_func) for a in range(self.__Ny)])
+        Jm = np.stack([mean_jacobian(self.__hyper[a], Z, self.__mean_func) for a in range(self.__Ny)], 1)
+        mean = mean + M
+        if jac is not None:
+            jfull = jac + Jm
+            if cov is not None and method == 'TA' and Sigma is not None:
+                S = np.broadcast_to(np.asarray(Sigma, dtype=np.float64), (Z.shape[0], self.__Nx, self.__Nx)) \
+                    if np.ndim(Sigma) == 2 else np.asarray(Sigma, dtype=np.float64)
+                cov = cov + np.einsum('had,hde,hbe->hab', jfull, S, jfull) - np.einsum('had,hde,hbe->hab', jac, S, jac)
+            jac = jfull
+        return mean, var, cov, (jac if want_jac else None)
 
     def predict_batch(self, x, u, cov=None, method=None):
         """Horizon batch: x:(H,Ny) u:(H,Nu) cov:(Nx,Nx)|(H,Nx,Nx)|None ->

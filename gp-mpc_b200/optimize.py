@@ -16,17 +16,7 @@ import time
 import numpy as np
 
 
-def count_mean_params(meanFunc, Nx):
-    """optimize.py:402-412 (same names, same NameError)."""
-    if meanFunc == 'zero':
-        return 0
-    if meanFunc == 'const':
-        return 1
-    if meanFunc == 'linear':
-        return Nx + 1
-    if meanFunc == 'polynomial':
-        return 2 * Nx + 1
-    raise NameError('No mean function called: ' + meanFunc)
+from .mean_functions import count_mean_params, mean_bounds, mean_design
 
 
 def bounds_and_init(X, y, fixed_bounds=False):
@@ -61,16 +51,22 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
     # here) the objective ignores them (calc_NLL_numpy reads hyper[:Nx+2] only, optimize.py:337-340;
     # "only support a zero-mean function", :377-379), their bounds are set after `bounds` was built
     # (:435-460) and therefore never reach SLSQP, so they stay at their initial value 0 and the
-    # fitted prior mean is identically zero.  That behaviour is reproduced: zero columns.
+    # fitted prior mean is identically zero.  That behaviour is the default here: zero columns.
+    # optimizer_opts={'fit_mean': True} instead fits them jointly with the kernel parameters on the
+    # objective of the reference's CasADi/IPOPT twin (calc_NLL, optimize.py:22-97: NLL of the
+    # residual y - m(X)), with the mean bounds of optimize.py:452-459; the extra gradient block is
+    # d NLL / d params = -Phi^T alpha (m = Phi params is linear in its parameters).
     h_m = count_mean_params(meanFunc, X.shape[1])
     N, Nx = X.shape
     options = {'disp': False, 'maxiter': 10000}
     jac_mode = 'analytic'
     fixed_bounds = False
+    fit_mean = False
     if optimizer_opts is not None:
         optimizer_opts = dict(optimizer_opts)
         jac_mode = optimizer_opts.pop('jac', jac_mode)
         fixed_bounds = bool(optimizer_opts.pop('fixed_bounds', False))
+        fit_mean = bool(optimizer_opts.pop('fit_mean', False)) and h_m > 0
         options.update(optimizer_opts)
     if jac_mode not in ('analytic', 'fd'):
         raise ValueError("optimizer_opts['jac'] must be 'analytic' or 'fd'")
@@ -85,7 +81,21 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
         if hyper_init is not None:
             init = np.asarray(hyper_init, dtype=np.float64)[a, :Nx + 2].copy()
 
+        if fit_mean:
+            from ._lib import GET_ALPHA_NLML
+            Phi = mean_design(X, meanFunc)
+            bounds = np.vstack([bounds, mean_bounds(Y[:, a], Nx, meanFunc)])
+            init = np.concatenate([init[:Nx + 2], np.zeros(h_m) if hyper_init is None
+                                   else np.asarray(hyper_init, dtype=np.float64)[a, Nx + 2:Nx + 2 + h_m]])
+            init = np.clip(init, bounds[:, 0], bounds[:, 1])
+
         def fun(theta, a=a):
+            if fit_mean:
+                engine.set_y(a, Y[:, a] - Phi @ theta[Nx + 2:])
+                if jac_mode != 'analytic':
+                    return engine.nlml(a, theta[:Nx + 2], grad=False)
+                nll, g = engine.nlml(a, theta[:Nx + 2], grad=True)
+                return nll, np.concatenate([g, -Phi.T @ engine.get(GET_ALPHA_NLML, a)])
             if jac_mode == 'analytic':
                 return engine.nlml(a, theta, grad=True)
             return engine.nlml(a, theta, grad=False)
@@ -97,7 +107,9 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
                        bounds=bounds, tol=1e-12)
         if verbose:
             print("* State %d:  %f s" % (a, time.time() - t0))
-        rows[k, :Nx + 2] = res.x
+        rows[k, :len(res.x)] = res.x
+        if fit_mean:
+            engine.set_y(a, Y[:, a])
     if verbose:
         print('----------------------------------------')
     return rows

@@ -49,7 +49,8 @@ enum {
     GPMPC_GET_INVK = 2,    /* (N,N) K^-1, symmetric                             (optimize.py:489-490) */
     GPMPC_GET_K = 3,       /* (N,N) K + sn2 I                                   (optimize.py:480-482) */
     GPMPC_GET_LOGDET = 4,  /* (1,)  2 sum log L_ii                              (optimize.py:352) */
-    GPMPC_GET_LINV = 5     /* (N,N) L^-1 lower                                  (optimize.py:489 invL) */
+    GPMPC_GET_LINV = 5,    /* (N,N) L^-1 lower                                  (optimize.py:489 invL) */
+    GPMPC_GET_ALPHA_NLML = 6 /* (N,) alpha of the last gpmpc_nlml evaluation for that output (mean-parameter gradient) */
 };
 
 /* selector of gpmpc_profile */
@@ -77,6 +78,11 @@ int gpmpc_set_data(gpmpc_handle_t h, const double* X, const double* Y);
 
 /* hyper:(Ny,ld) host, ld >= Nx+2; only the owned rows are used (gp_class.py:134-142). */
 int gpmpc_set_hyper(gpmpc_handle_t h, const double* hyper, int ld);
+
+/* Replace the target vector of global output a with y (N doubles, host): the GP class passes the
+ * residual y - m(X) of a prior mean function (alpha = K^-1 (y - m(X)), optimize.py:492-494;
+ * get_mean_function, gp_functions.py:25-69).  Invalidates the factorisation. */
+int gpmpc_set_y(gpmpc_handle_t h, int a, const double* y);
 
 /* K = covSEard(X,X) + sn2 I for global output a into K_out:(N,N) host (may be NULL:
  * build only).  Replaces calc_cov_matrix + noise + symmetrise, optimize.py:303-319,

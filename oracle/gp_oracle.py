@@ -98,6 +98,29 @@ def calc_cov_matrix(X, ell, sf2):
     return covSEard_expanded(X, X, ell, sf2)
 
 
+def mean_function(hyper_a, X, func='zero'):
+    """``get_mean_function`` ``gp_functions.py:25-69`` evaluated numerically: parameters are the tail
+    of the hyper row -- const: m = hyp[-1] (:46-50); linear: a = hyp[-Nx-1:-1], b = hyp[-1],
+    m = a^T x + b (:51-56); polynomial: a = hyp[-2Nx-1:-Nx-1], b = hyp[-Nx-1:-1], c = hyp[-1],
+    m = a^T x^2 + b^T x + c (:57-63).  X:(n,Nx) -> (n,)."""
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    hyp = np.asarray(hyper_a, dtype=np.float64).reshape(-1)
+    n, Nx = X.shape
+    m = np.zeros(n)
+    for i in range(n):                                   # the reference's per-point loop
+        if func == 'zero':
+            m[i] = 0.0
+        elif func == 'const':
+            m[i] = hyp[-1]
+        elif func == 'linear':
+            m[i] = np.dot(hyp[-Nx - 1:-1], X[i]) + hyp[-1]
+        elif func == 'polynomial':
+            m[i] = np.dot(hyp[-2 * Nx - 1:-Nx - 1], X[i] ** 2) + np.dot(hyp[-Nx - 1:-1], X[i]) + hyp[-1]
+        else:
+            raise NameError('No mean function called: ' + func)
+    return m
+
+
 # ----------------------------------------------------------------------------
 # a2/a3  K assembly + Cholesky with the single 1e-8 jitter retry
 # ----------------------------------------------------------------------------
@@ -194,7 +217,7 @@ def calc_NLL_grad_analytic(hyper_a, X, y):
 # ----------------------------------------------------------------------------
 # a5  post-fit block: chol, invK, alpha per output
 # ----------------------------------------------------------------------------
-def postfit(X, Y, hyper, lapack_general_solve=True):
+def postfit(X, Y, hyper, lapack_general_solve=True, mean_func='zero'):
     """``optimize.py:472-494`` (twins ``:267-285``, ``gp_class.py:516-537``).
 
     hyper:(Ny, Nx+2[+mean params]); zero prior mean ('zero' mean function, the
@@ -215,11 +238,11 @@ def postfit(X, Y, hyper, lapack_general_solve=True):
         if lapack_general_solve or _solve_tri is None:
             invL = np.linalg.solve(L, np.eye(N))                         # :489
             invK[a] = np.linalg.solve(L.T, invL)                         # :490
-            alpha[a] = np.linalg.solve(L.T, np.linalg.solve(L, Y[:, a]))  # :494
+            alpha[a] = np.linalg.solve(L.T, np.linalg.solve(L, Y[:, a] - mean_function(hyper[a], X, mean_func)))  # :492-494
         else:
             invL = _solve_tri(L, np.eye(N), lower=True)
             invK[a] = _solve_tri(L.T, invL, lower=False)
-            alpha[a] = _solve_tri(L.T, _solve_tri(L, Y[:, a], lower=True), lower=False)
+            alpha[a] = _solve_tri(L.T, _solve_tri(L, Y[:, a] - mean_function(hyper[a], X, mean_func), lower=True), lower=False)
         chol[a] = L                                                      # :491
     return dict(chol=chol, alpha=alpha, invK=invK, jitter=jit)
 

@@ -34,6 +34,9 @@ class OracleEngine:
     def set_hyper(self, hyper):
         self.hyper = np.array(hyper)
 
+    def set_y(self, a, y):
+        self.Y[:, a] = np.asarray(y)
+
     def set_option(self, name, value):
         pass
 

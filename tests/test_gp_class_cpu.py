@@ -88,3 +88,49 @@ def test_validate_matches_oracle_and_prints_banners(capsys):
     assert '# Validation of GP model' in out and '* Standardized mean squared error:' in out
     gp.print_hyper_parameters()
     assert '# Hyper-parameters' in capsys.readouterr().out
+
+
+def test_prior_mean_functions_follow_the_reference():
+    """get_mean_function (gp_functions.py:25-69): parameter layout at the tail of the hyper row,
+    alpha on the residual y - m(X) (optimize.py:492-494), prediction without m(z) by default (q2)
+    and with it under the flag.  Host logic only: the engine is the oracle-backed stand-in."""
+    import gp_mpc_b200
+    from gp_mpc_b200 import mean_functions as mf
+    from tests._fake_engine import OracleEngine
+    rng = np.random.default_rng(2)
+    p = orc.synthetic_problem(30, 3, 2, config_id=21, H=5)
+    Nx = 3
+    for func, h_m in (('const', 1), ('linear', Nx + 1), ('polynomial', 2 * Nx + 1)):
+        assert mf.count_mean_params(func, Nx) == h_m
+        hyper = np.hstack([p['hyper'], 0.3 * rng.standard_normal((2, h_m))])
+        for a in range(2):
+            m_ref = orc.mean_function(hyper[a], p['X'], func)
+            np.testing.assert_allclose(mf.mean_function(hyper[a], p['X'], func), m_ref, rtol=1e-13, atol=1e-14)
+            np.testing.assert_allclose(mf.mean_design(p['X'], func) @ hyper[a, Nx + 2:], m_ref, rtol=1e-13, atol=1e-14)
+            # Jacobian of the mean vs central differences
+            Jm = mf.mean_jacobian(hyper[a], p['Z'], func)
+            for d in range(Nx):
+                e = np.zeros(Nx); e[d] = 1e-6
+                fd = (mf.mean_function(hyper[a], p['Z'] + e, func) - mf.mean_function(hyper[a], p['Z'] - e, func)) / 2e-6
+                np.testing.assert_allclose(Jm[:, d], fd, rtol=1e-6, atol=1e-8)
+        post = orc.postfit(p['X'], p['Y'], hyper, lapack_general_solve=False, mean_func=func)
+        kw = dict(hyper=dict(hyper=hyper), normalize=False, mean_func=func, engine_factory=OracleEngine)
+        gp = gp_mpc_b200.GP(p['X'], p['Y'], **kw)
+        np.testing.assert_allclose(gp.get_alpha(), post['alpha'], rtol=1e-9, atol=1e-12)
+        assert gp.get_hyper_parameters()['mean'].shape == (2, 1 + h_m)          # q1: includes sn
+        mo, vo = orc.gp_mean_var(p['X'], hyper, post['alpha'], post['chol'], p['Z'])
+        Ny = 2
+        mean, cov = gp.predict_batch(p['Z'][:, :Ny], p['Z'][:, Ny:], p['Sigma'])
+        np.testing.assert_allclose(mean, mo, rtol=1e-9, atol=1e-12)             # q2: no m(z) added
+        gp2 = gp_mpc_b200.GP(p['X'], p['Y'], prior_mean_in_predict=True, **kw)
+        mean2, cov2 = gp2.predict_batch(p['Z'][:, :Ny], p['Z'][:, Ny:], p['Sigma'])
+        M = np.column_stack([orc.mean_function(hyper[a], p['Z'], func) for a in range(2)])
+        np.testing.assert_allclose(mean2, mo + M, rtol=1e-9, atol=1e-12)
+        Jfull = orc.gp_mean_jac(p['X'], hyper, post['alpha'], p['Z']) + np.stack([mf.mean_jacobian(hyper[a], p['Z'], func) for a in range(2)], 1)
+        np.testing.assert_allclose(cov2, orc.ta_cov(vo, Jfull, p['Sigma']), rtol=1e-8, atol=1e-14)
+        A, B = gp2.discrete_linearize(p['Z'][0, :Ny], p['Z'][0, Ny:], None)
+        np.testing.assert_allclose(np.hstack([A, B]), Jfull[0], rtol=1e-9, atol=1e-12)
+    with pytest.raises(NameError):
+        mf.count_mean_params('cubic', 3)
+    lbub = mf.mean_bounds(np.array([-1.0, -3.0]), 3, 'linear')                   # inverted reference interval is sorted
+    assert (lbub[:, 0] <= lbub[:, 1]).all() and lbub.shape == (4, 2)

@@ -360,7 +360,7 @@ def test_casadi_external_entry_points():
     mean_cm = np.empty((Nt, Ny)); cov_cm = np.empty((Nt, Ny, Ny))
     call(lib.gp_b200, [z_cm, s_cm], [mean_cm, cov_cm])
     mean, var, cov, jac = eng.predict(Z, Sg, Lb.METHOD_TA)
-    assert np.array_equal(mean_cm, mean) and np.array_equal(cov_cm, np.transpose(cov, (0, 2, 1)))
+    assert np.array_equal(mean_cm, mean) and np.array_equal(cov_cm, np.transpose(cov, (0, 2, 1)))   # column-major blocks
     g = eng.predict_grad(Z, Sg, Lb.METHOD_TA)
 
     def ccs(ptr):
@@ -469,6 +469,57 @@ def test_nlml_gradient_vs_oracle():
         assert relinf(g, orc.calc_NLL_grad_analytic(th, p['X'], p['Y'][:, a])) < 1e-8
         assert relinf(g, orc.calc_NLL_grad_fd(th, p['X'], p['Y'][:, a])) < 1e-5
     eng.close()
+
+
+def test_prior_mean_functions_on_the_gpu():
+    """get_mean_function (gp_functions.py:25-69) through the engine: alpha on the residual y - m(X)
+    (optimize.py:492-494) for given mean parameters; the q2 flag; and the joint fit of kernel + mean
+    parameters ('fit_mean', objective of the CasADi twin optimize.py:22-97) lowers the NLL of the
+    residual below the zero-mean fit on data with a linear trend."""
+    import gp_mpc_b200
+    from gp_mpc_b200 import mean_functions as mf
+    rng = np.random.default_rng(6)
+    p = orc.synthetic_problem(150, 3, 2, config_id=41, H=7)
+    X = p['X']; Y = p['Y'] + X @ np.array([[0.8, -0.3], [0.1, 0.5], [-0.4, 0.2]]) + np.array([0.7, -1.1])
+    hyper = np.hstack([p['hyper'], 0.2 * rng.standard_normal((2, 4))])
+    post = orc.postfit(X, Y, hyper, lapack_general_solve=False, mean_func='linear')
+    gp = gp_mpc_b200.GP(X, Y, hyper=dict(hyper=hyper), normalize=False, mean_func='linear')
+    assert relinf(gp.get_alpha(), post['alpha']) < 1e-7 and relinf(gp.get_chol(), post['chol']) < 1e-10
+    mo, vo = orc.gp_mean_var(X, hyper, post['alpha'], post['chol'], p['Z'])
+    mean, cov = gp.predict_batch(p['Z'][:, :2], p['Z'][:, 2:], p['Sigma'])
+    assert relinf(mean, mo) < TOL                                   # q2: m(z) is not added back
+    gp_f = gp_mpc_b200.GP(X, Y, hyper=dict(hyper=hyper), normalize=False, mean_func='linear', prior_mean_in_predict=True)
+    mean_f, _ = gp_f.predict_batch(p['Z'][:, :2], p['Z'][:, 2:], p['Sigma'])
+    M = np.column_stack([orc.mean_function(hyper[a], p['Z'], 'linear') for a in range(2)])
+    assert relinf(mean_f, mo + M) < TOL
+    gp.close(); gp_f.close()
+    # joint fit: gradient block of the mean parameters vs central differences of the restated NLL
+    eng = _engine(150, 3, 2); eng.set_data(X, Y)
+    Phi = mf.mean_design(X, 'linear')
+    th = hyper[0].copy()
+    eng.set_y(0, Y[:, 0] - Phi @ th[5:])
+    nll, g = eng.nlml(0, th[:5], grad=True)
+    gm = -Phi.T @ eng.get(_L().GET_ALPHA_NLML, 0)
+    ref = lambda t: orc.calc_NLL(t[:5], X, Y[:, 0] - Phi @ t[5:], False)
+    assert nll == pytest.approx(ref(th), rel=1e-10)
+    for j in range(4):
+        e = np.zeros(9); e[5 + j] = 1e-6
+        assert gm[j] == pytest.approx((ref(th + e) - ref(th - e)) / 2e-6, rel=1e-5, abs=1e-6)
+    eng.close()
+    opts = {'maxiter': 200, 'fixed_bounds': True}
+    gp0 = gp_mpc_b200.GP(X, Y, normalize=False, mean_func='linear', optimizer_opts=dict(opts))
+    h0 = np.column_stack([gp0.get_hyper_parameters()['length_scale'], np.sqrt(gp0.get_hyper_parameters()['signal_var']),
+                          gp0.get_hyper_parameters()['mean']])
+    assert h0.shape == (2, 9) and np.all(h0[:, 5:] == 0.0)          # reference numeric path: mean parameters stay 0
+    gp1 = gp_mpc_b200.GP(X, Y, normalize=False, mean_func='linear', optimizer_opts=dict(opts, fit_mean=True))
+    h1 = np.column_stack([gp1.get_hyper_parameters()['length_scale'], np.sqrt(gp1.get_hyper_parameters()['signal_var']),
+                          gp1.get_hyper_parameters()['mean']])
+    assert np.abs(h1[:, 5:8]).max() <= 1e-2 + 1e-12                  # slope bounds of optimize.py:458-459
+    for a in range(2):
+        n0 = orc.calc_NLL(h0[a, :5], X, Y[:, a], False)
+        n1 = orc.calc_NLL(h1[a, :5], X, Y[:, a] - Phi @ h1[a, 5:], False)
+        assert n1 <= n0 + 1e-6 * abs(n0)
+    gp0.close(); gp1.close()
 
 
 # ------------------------------------------------------------------ the GP class (drop-in boundary)

@@ -15,7 +15,7 @@ for nout in (1, 8):
     eng = gp_mpc_b200.Engine(N, 10, nout, device=0)
     eng.set_data(w['X'], w['Y']); eng.set_hyper(w['hyper']); eng.factorize()
     eng.predict(w['Z'], w['Sigma'], L.METHOD_TA)
-    for ctas in (0, 148, 222, 296, 592):
+    for ctas in (0, 296, 444, 592, 888, 1184, 1776):
         eng.set_option('predict_ctas', ctas)
         ms = eng.profile(L.PROF_TRIGEMM, n=H, reps=20)
         bal = eng.profile_balance(H)
