@@ -92,13 +92,13 @@ struct gpmpc_handle_s {
     double *dU = nullptr, *dKinv = nullptr, *dGradPart = nullptr, *dGrad = nullptr;
     bool has_data = false, has_hyper = false, factorized = false;
     // EM scratch
-    double *dKinvAll = nullptr, *dEMP = nullptr, *dEmE = nullptr, *dEmF = nullptr, *dEmW = nullptr, *dEmIJ = nullptr;
-    double *dEmMeanPart = nullptr, *dEmPart = nullptr;
-    bool em_kinv_valid = false; int emHcap = 0;
+    double *dEmTr = nullptr, *dEMP = nullptr, *dEmE = nullptr, *dEmF = nullptr, *dEmW = nullptr, *dEmIJ = nullptr;
+    double *dEmMeanPart = nullptr, *dEmPart = nullptr, *dEmLQ = nullptr;
+    int emHcap = 0;
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
     std::vector<int> jitter_used;
-    int opt_refine = 0, opt_gemm_variant = 3, opt_leaf_variant = 1, opt_small_tiles = 592;   // 128x64-tile count below which 64x32 tiles are used
+    int opt_refine = 0, opt_gemm_variant = 3, opt_leaf_variant = 2, opt_small_tiles = 592;   // 128x64-tile count below which 64x32 tiles are used
     // comm
     nccl_comm_t comm = nullptr; int rank = 0, world = 1;
     // peer (CUDA IPC) exchange: [flags: 2*MAXW u64][gather buffer parity 0][parity 1]
@@ -189,14 +189,18 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
         if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
             CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_N * LEAF_LD * 8));
             CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_DOUBLES * 8));
+            CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF3_SMEM_DOUBLES * 8));
             conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
         }
         if (h->opt_leaf_variant == 0)
             leaf_potrf_trtri_kernel<<<batch, 256, LEAF_N * LEAF_LD * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
                                                                               Li + (long long)off * ld + off, ld, sLi, dInfo, off);
-        else
+        else if (h->opt_leaf_variant == 1)
             leaf_potrf_trtri_v2_kernel<<<batch, 256, LF_SMEM_DOUBLES * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
                                                                                 Li + (long long)off * ld + off, ld, sLi, dInfo, off);
+        else
+            leaf_potrf_trtri_v3_kernel<<<batch, 256, LF3_SMEM_DOUBLES * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
+                                                                                 Li + (long long)off * ld + off, ld, sLi, dInfo, off);
         CUDA_TRY(cudaGetLastError());
         return GPMPC_OK;
     }
@@ -451,7 +455,7 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     if (h->hPeerStatus) cudaFreeHost(h->hPeerStatus);
     double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
                       h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dR2, h->dCovV, h->dCovOut, h->dUall, h->dBeta, h->dPDV, h->dPH, h->dGradOut, h->dG, h->dIn, h->dOut, h->dU, h->dKinv, h->dGradPart, h->dGrad,
-                      h->dKinvAll, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
+                      h->dEmTr, h->dEmLQ, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
     if (h->hPinned) cudaFreeHost(h->hPinned);
@@ -617,7 +621,7 @@ extern "C" int gpmpc_factorize(gpmpc_handle_t h, double jitter, int* info)
     CUDA_TRY(cudaMemcpyAsync(res.data(), h->dRes, 2 * nl * 8, cudaMemcpyDeviceToHost, h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
     for (int a = 0; a < nl; ++a) { h->logdet[a] = res[2 * a]; h->yalpha[a] = res[2 * a + 1]; }
-    h->factorized = true; h->em_kinv_valid = false; h->u_valid = false;
+    h->factorized = true; h->u_valid = false;
     return GPMPC_OK;
 }
 
@@ -920,7 +924,8 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
     as.flags = use_peers ? reinterpret_cast<const unsigned long long*>(h->dPeerBlock) + (h->peer_step & 1) * GPMPC_MAXW : nullptr;
     as.world = h->world; as.step = h->peer_step; as.status = h->dPeerStatus; as.timeout_clocks = timeout_clocks;
     // one chunk and no NCCL call in between: the product kernel's last CTA assembles too (2 launches per step)
-    const bool fused_assemble = (H <= HB) && !nccl_gather;
+    // (its 8 warps each need 2 Ny Nx + Ny doubles of the pipeline's shared memory: >= 68 KB at the smallest tile)
+    const bool fused_assemble = (H <= HB) && !nccl_gather && (8 * (2 * h->Ny * Nx + h->Ny) * 8 <= 64 * 1024);
     for (int h0 = 0; h0 < H; h0 += HB) {
         const int Hc = std::min(HB, H - h0);
         const int bm = (Hc + 7) / 8 * 8;
@@ -1046,7 +1051,7 @@ static cudaError_t launch_em_prep(gpmpc_handle_t h, int npairs, const double* dz
 {
     dim3 g(nblk, h->Ny + npairs);
     em_prep_kernel<NXP><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->Ny, npairs, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
-                                              dz, dEMP, h->dEmMeanPart, nblk, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->Npad);
+                                              dz, dEMP, h->dEmMeanPart, nblk, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->Npad, h->dEmLQ);
     return cudaGetLastError();
 }
 
@@ -1059,27 +1064,21 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
     const int npairs = Ny * (Ny + 1) / 2;
     if (npairs > 1024) { set_error(h, "EM supports Ny <= 44"); return GPMPC_ERR_ARG; }
     const size_t per = (size_t)Ny * (nn + 1) + (size_t)npairs * (nn + 3);
-    const int nblk = (np + 255) / 256, T = (h->N + 63) / 64;
-    if (!h->dKinvAll) {
-        ALLOC(h->dKinvAll, (long long)Ny * slab(h));
+    const int nblk = (np + 255) / 256, T = (h->N + 63) / 64, Tq = np / 64, ntr = Tq * (Tq + 1) / 2;
+    if (!h->dEmTr) {
+        ALLOC(h->dEmTr, (long long)Ny * ntr);
+        ALLOC(h->dEmLQ, (long long)Ny * np);
         ALLOC(h->dEmE, (long long)npairs * np); ALLOC(h->dEmF, (long long)npairs * np);
         ALLOC(h->dEmW, (long long)npairs * Nx * np); ALLOC(h->dEmIJ, (long long)npairs * Nx * np);
         ALLOC(h->dEmMeanPart, (long long)Ny * nblk); ALLOC(h->dEmPart, (long long)npairs * T * T);
     }
+    { int rcs = ensure_nlml_scratch(h); if (rcs) return rcs; }      // dKinv <- Q_aa, dU <- L^-1 Q_aa (one slab each)
     if (H > h->emHcap) {
         CUDA_TRY(cudaStreamSynchronize(h->st));
         if (h->dEMP) cudaFree(h->dEMP);
         h->dEMP = nullptr;
         ALLOC(h->dEMP, (long long)H * per);
         h->emHcap = H;
-    }
-    if (!h->em_kinv_valid) {       // beta beta^T - K^-1 needs the dense inverse (:409-411)
-        for (int a = 0; a < Ny; ++a) {
-            int rc = compute_kinv(h, a);
-            if (rc) return rc;
-            CUDA_TRY(cudaMemcpyAsync(h->dKinvAll + (long long)a * slab(h), h->dKinv, slab(h) * 8, cudaMemcpyDeviceToDevice, h->st));
-        }
-        h->em_kinv_valid = true;
     }
     std::vector<double> emp((size_t)H * per);
     for (int p = 0; p < H; ++p) {
@@ -1094,10 +1093,28 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
         cudaError_t e = (Nx <= 8) ? launch_em_prep<8>(h, npairs, dz, dP, nblk)
                       : (Nx <= 16) ? launch_em_prep<16>(h, npairs, dz, dP, nblk) : launch_em_prep<32>(h, npairs, dz, dP, nblk);
         CUDA_TRY(e);
-        em_pair_kernel<<<dim3(T, T, npairs), 256, 2 * Nx * 64 * 8, h->st>>>(h->N, Nx, Ny, dP, h->dAlpha, np, h->dKinvAll, np, slab(h),
-                                                                          h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmPart);
+        em_pair_kernel<<<dim3(T, T, npairs), 256, 2 * Nx * 64 * 8, h->st>>>(h->N, Nx, Ny, dP, h->dAlpha, np,
+                                                                          h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmLQ, h->dEmPart, 0, 0, nullptr, 0);
         CUDA_TRY(cudaGetLastError());
+        // E[var] term of the diagonal pairs, Cholesky-based: t tr(K^-1 Q_aa) = t tr(L^-1 Q_aa L^-T)
+        for (int a = 0; a < Ny; ++a) {
+            const int paa = a * (a + 1) / 2 + a;
+            em_pair_kernel<<<dim3(Tq, Tq, 1), 256, 2 * Nx * 64 * 8, h->st>>>(h->N, Nx, Ny, dP, h->dAlpha, np,
+                                                                          h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmLQ, nullptr, 1, paa, h->dKinv, np);
+            CUDA_TRY(cudaGetLastError());
+            GemmParams gp;
+            memset(&gp, 0, sizeof(gp));
+            gp.A = h->dLi + (long long)a * slab(h); gp.lda = np;
+            gp.B = h->dKinv; gp.ldb = np;                 // Q symmetric: row-major (j,k) storage is the NT operand
+            gp.C = h->dU; gp.ldc = np;
+            gp.mt = np / 128; gp.nt = np / 128; gp.K = np; gp.alpha = 1.0; gp.beta = 0.0;
+            gp.kflags = GEMM_KI_LE; gp.lower = 1;
+            CUDA_TRY(gemm128(h, true, gp, 1));
+            em_trdot_kernel<<<ntr, 256, 0, h->st>>>(h->dU, h->dLi + (long long)a * slab(h), np, h->dEmTr + (long long)a * ntr);
+            CUDA_TRY(cudaGetLastError());
+        }
         em_finalize_kernel<<<1, 1024, 0, h->st>>>(Nx, Ny, npairs, dP, h->dHyp, Nx + 2, h->dEmMeanPart, nblk, h->dEmPart, T * T,
+                                                   h->dEmTr, ntr,
                                                    h->dMean + (size_t)p * Ny, h->dVar + (size_t)p * Ny, h->dCov + (size_t)p * Ny * Ny);
         CUDA_TRY(cudaGetLastError());
     }
@@ -1342,7 +1359,7 @@ extern "C" int gpmpc_append(gpmpc_handle_t h, const double* x_new, const double*
             return GPMPC_ERR_NOTPD;
         }
     h->N = N + 1;
-    h->em_kinv_valid = false; h->u_valid = false;
+    h->u_valid = false;
     rc = launch_alpha(h, 0, nl);
     if (rc) return rc;
     std::vector<double> res(2 * nl);

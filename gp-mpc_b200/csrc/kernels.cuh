@@ -423,6 +423,268 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
     LEAF_STAMP(14);
 }
 
+// ---------------------------------------------------------------------------------------
+// a3 leaf v3.  Same contract as v2; the 128-pivot dependency chain is the only thing left on
+// the critical path (r2b profile of v2: 74 us = 140k cycles, of which the warp-level 16x16
+// potrf+trtri 35 %, the Dinv panel products 13 %, the block load 10 %, the serial inverse
+// assembly 16 %):
+//   * per 16-column block step the chain is  potrf16 (warp 0, registers + shuffles, fp32-seeded
+//     rsqrt: ~170 cycles per pivot)  ->  panel by FORWARD SUBSTITUTION with the 16x16 factor (one
+//     thread per row, the factor is broadcast from shared memory; no 16x16 inverse needed)  ->
+//     DMMA update of the next block column;
+//   * everything else runs beside it: warps 2..7 finish the trailing update of the previous step
+//     and warp 1 inverts the previous 16x16 diagonal block (needed only by the inverse assembly)
+//     while warp 0 factorises the next one;
+//   * the triangular inverse is assembled by recursive doubling with four independent DMMA
+//     accumulator chains per warp (v2 ran one dependent chain per 8x8 tile);
+//   * 16-byte global loads / stores.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double rsqrt_seeded(double d)
+{
+    // MUFU.RSQ (fp32, ~2^-22) + two Newton steps in fp64: relative error ~1e-15; arguments outside
+    // fp32's comfortable range take the library routine
+    if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+    double y = (double)rsqrtf((float)d);
+    double e = fma(-(d * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(d * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return y;
+}
+
+// 16x16 Cholesky in registers (lane r and r+16 hold row r); writes the factor back (lower part) and
+// the reciprocal pivots to ipd[16]
+__device__ __forceinline__ void warp_potrf16(double* D, double* ipd, int* info, int info_val0, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const int r = lane & 15;
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = D[r * LF_LD + k];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const double d = __shfl_sync(full, a[j], j);
+        if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, info_val0 + j + 1);
+        double y = rsqrt_seeded(d);
+        double pv = d * y;
+        pv = fma(fma(-pv, pv, d), 0.5 * y, pv);             // sqrt(d) to ~0.5 ulp
+        if (!(d > 0.0)) { pv = sqrt(d); y = 1.0 / pv; }     // keep NaN/inf propagation of the plain formula
+        a[j] = (r == j) ? pv : a[j] * y;
+        if (lane == 0) ipd[j] = y;
+#pragma unroll
+        for (int k = j + 1; k < 16; ++k) {
+            const double lkj = __shfl_sync(full, a[j], k);
+            a[k] = fma(-a[j], lkj, a[k]);                  // meaningful for r >= k; upper part is never read
+        }
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (k <= r) D[r * LF_LD + k] = a[k];
+    }
+    __syncwarp();
+}
+
+// inverse of a factorised 16x16 block (off the critical path): lane r computes column r by forward
+// substitution; two partial sums shorten the dependent FMA chain
+__device__ __forceinline__ void warp_trtri16(const double* D, const double* ipd, double* Dinv, int lane)
+{
+    const int r = lane & 15;
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double l = D[i * LF_LD + k];              // broadcast read
+            if (k & 1) s1 = fma(l, x[k], s1); else s0 = fma(l, x[k], s0);
+        }
+        const double ip = ipd[i];
+        x[i] = (i < r) ? 0.0 : ((i == r) ? ip : -(s0 + s1) * ip);
+        if (lane < 16) Dinv[i * 17 + r] = x[i];
+    }
+}
+
+#define LF3_SMEM_DOUBLES (LEAF_N * LF_LD + 8 * 16 * 17 + 8 * 16 + 64 * 68 + 64)
+__global__ void __launch_bounds__(256, 1)
+leaf_potrf_trtri_v3_kernel(double* __restrict__ A, int lda, long long sA,
+                           double* __restrict__ Li, int ldi, long long sLi,
+                           int* __restrict__ info, int info_base)
+{
+    extern __shared__ __align__(16) double S[];                // [128][132]
+    double* DinvAll = S + LEAF_N * LF_LD;                      // [8][16][17]
+    double* ipdAll = DinvAll + 8 * 16 * 17;                    // [8][16] reciprocal pivots
+    double* T1 = ipdAll + 8 * 16;                              // inverse-assembly scratch: npair x sz x (sz+4) <= 64 x 68
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    double* Ab = A + (long long)blockIdx.x * sA;
+    double* Lb = Li + (long long)blockIdx.x * sLi;
+    LEAF_STAMP(0);
+    {   // 128 x 128 block -> shared memory, 16-byte loads, 16 in flight per thread
+        double2 v[16];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int idx = tid + 256 * (q + 16 * half);       // double2 index: row = idx >> 6, col2 = idx & 63
+                v[q] = *reinterpret_cast<const double2*>(Ab + (long long)(idx >> 6) * lda + 2 * (idx & 63));
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int idx = tid + 256 * (q + 16 * half);
+                *reinterpret_cast<double2*>(S + (idx >> 6) * LF_LD + 2 * (idx & 63)) = v[q];
+            }
+        }
+    }
+    __syncthreads();
+    LEAF_STAMP(1);
+
+    auto panel = [&](int c0, const double* ipd) {
+        // rows below the diagonal block: x = a D^-T by forward substitution (x_j = (a_j - sum_{k<j} x_k L_jk)/L_jj)
+        const int rr = c0 + LF_NB + tid;
+        if (rr < LEAF_N) {
+            double* row = S + rr * LF_LD + c0;
+            const double* Dk = S + c0 * LF_LD + c0;
+            double a[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = row[k];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                a[j] *= ipd[j];
+#pragma unroll
+                for (int k = j + 1; k < 16; ++k) a[k] = fma(-a[j], Dk[k * LF_LD + j], a[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) row[k] = a[k];
+        }
+    };
+    auto update_tile = [&](int c0, int ti, int tj) {      // C(8x8 at tile ti,tj of the trailing block) -= P_R P_C^T
+        const int R0 = c0 + LF_NB + 8 * ti, C0 = c0 + LF_NB + 8 * tj;
+        double* cp = S + (R0 + g) * LF_LD + C0 + 2 * t;
+        double acc0 = cp[0], acc1 = cp[1];
+        const double* pa = S + (R0 + g) * LF_LD + c0 + t;
+        const double* pb = S + (C0 + g) * LF_LD + c0 + t;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) dmma884(acc0, acc1, -pa[kk * 4], pb[kk * 4]);
+        cp[0] = acc0; cp[1] = acc1;
+    };
+    if (warp == 0) warp_potrf16(S, ipdAll, info + blockIdx.x, info_base, lane);
+    __syncthreads();
+    panel(0, ipdAll);
+    __syncthreads();
+    LEAF_STAMP(2);
+    for (int kb = 0; kb < 7; ++kb) {
+        const int c0 = kb * LF_NB, b0 = c0 + LF_NB;
+        const int nt8 = (LEAF_N - b0) >> 3;
+        // C1: the two 8-wide tile columns of the next block column
+        for (int tl = warp; tl < 2 * nt8; tl += 8) {
+            const int ti = tl >> 1, tj = tl & 1;
+            if (tj <= ti) update_tile(c0, ti, tj);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            warp_potrf16(S + b0 * LF_LD + b0, ipdAll + (kb + 1) * 16, info + blockIdx.x, info_base + b0, lane);
+        } else if (warp == 1) {
+            warp_trtri16(S + c0 * LF_LD + c0, ipdAll + kb * 16, DinvAll + kb * 16 * 17, lane);
+        } else {
+            // C2: tiles 2 <= tj <= ti < nt8 on warps 2..7
+            const int m = nt8 - 2;
+            const int ntile = m > 0 ? m * (m + 1) / 2 : 0;
+            for (int tl = warp - 2; tl < ntile; tl += 6) {
+                int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+                while (ti * (ti + 1) / 2 > tl) --ti;
+                while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+                const int tj = tl - ti * (ti + 1) / 2;
+                update_tile(c0, ti + 2, tj + 2);
+            }
+        }
+        __syncthreads();
+        panel(b0, ipdAll + (kb + 1) * 16);
+        __syncthreads();
+        LEAF_STAMP(3 + kb);
+    }
+    if (warp == 1) warp_trtri16(S + 112 * LF_LD + 112, ipdAll + 7 * 16, DinvAll + 7 * 16 * 17, lane);
+    // L out (exact zeros above the diagonal), 16-byte stores; warp 1 joins after its last 16x16 inverse
+    for (int idx = tid; idx < LEAF_N * LEAF_N / 2; idx += 256) {
+        const int r = idx >> 6, c = 2 * (idx & 63);
+        double2 v = *reinterpret_cast<const double2*>(S + r * LF_LD + c);
+        if (c > r) v.x = 0.0;
+        if (c + 1 > r) v.y = 0.0;
+        *reinterpret_cast<double2*>(Ab + (long long)r * lda + c) = v;
+    }
+    __syncthreads();
+    LEAF_STAMP(10);
+
+    // ---------------- triangular inverse by recursive doubling ----------------
+    {
+        const int r = tid >> 4, c = tid & 15;               // 16 x 16 threads
+        for (int kb = 0; kb < 8; ++kb)                      // exact zeros above the diagonal: DMMA k-ranges read them
+            S[(kb * 16 + r) * LF_LD + kb * 16 + c] = (c <= r) ? DinvAll[kb * 16 * 17 + r * 17 + c] : 0.0;
+    }
+    __syncthreads();
+    for (int sz = 16; sz < LEAF_N; sz <<= 1) {
+        const int npair = LEAF_N / (2 * sz), t8 = sz >> 3, ldt = sz + 4;
+        const int gw = (t8 < 4) ? t8 : 4;                   // tiles per group (same tile row, consecutive tile columns)
+        const int ngrp = npair * t8 * (t8 / gw);
+        // T1 = B * Ainv   (Ainv lower: k >= j; the group starts at its first column's k)
+        for (int gi = warp; gi < ngrp; gi += 8) {
+            const int per = t8 * (t8 / gw);
+            const int pr = gi / per, rem = gi % per, ti = rem / (t8 / gw), tj0 = (rem % (t8 / gw)) * gw;
+            const int p0 = pr * 2 * sz;
+            const double* pa = S + (p0 + sz + 8 * ti + g) * LF_LD + p0 + t;            // B rows
+            const double* pb = S + (p0 + t) * LF_LD + p0 + 8 * tj0 + g;                // Ainv[k][n]
+            double acc[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+            for (int k0 = 8 * tj0; k0 < sz; k0 += 4) {
+                const double av = pa[k0];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)       // column tile tj0+q only has k >= 8 (tj0+q): above that Ainv is zero by
+                    if (q < gw && k0 >= 8 * (tj0 + q))   // structure, but the storage there holds stale values
+                        dmma884(acc[q][0], acc[q][1], av, pb[k0 * LF_LD + 8 * q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < gw) {
+                    double* tp = T1 + pr * sz * ldt + (8 * ti + g) * ldt + 8 * (tj0 + q) + 2 * t;
+                    tp[0] = acc[q][0]; tp[1] = acc[q][1];
+                }
+        }
+        __syncthreads();
+        // X = -Cinv * T1  (Cinv lower: k <= i), written over B
+        for (int gi = warp; gi < ngrp; gi += 8) {
+            const int per = t8 * (t8 / gw);
+            const int pr = gi / per, rem = gi % per, ti = rem / (t8 / gw), tj0 = (rem % (t8 / gw)) * gw;
+            const int p0 = pr * 2 * sz;
+            const double* pa = S + (p0 + sz + 8 * ti + g) * LF_LD + p0 + sz + t;       // Cinv rows
+            const double* pb = T1 + pr * sz * ldt + t * ldt + 8 * tj0 + g;             // T1[k][n]
+            double acc[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+            for (int k0 = 0; k0 < 8 * ti + 8; k0 += 4) {
+                const double av = -pa[k0];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < gw) dmma884(acc[q][0], acc[q][1], av, pb[k0 * ldt + 8 * q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < gw) {
+                    double* xp = S + (p0 + sz + 8 * ti + g) * LF_LD + p0 + 8 * (tj0 + q) + 2 * t;
+                    xp[0] = acc[q][0]; xp[1] = acc[q][1];
+                }
+        }
+        __syncthreads();
+        LEAF_STAMP(sz == 16 ? 11 : (sz == 32 ? 12 : 13));
+    }
+    for (int idx = tid; idx < LEAF_N * LEAF_N / 2; idx += 256) {
+        const int r = idx >> 6, c = 2 * (idx & 63);
+        double2 v = *reinterpret_cast<const double2*>(S + r * LF_LD + c);
+        if (c > r) v.x = 0.0;
+        if (c + 1 > r) v.y = 0.0;
+        *reinterpret_cast<double2*>(Lb + (long long)r * ldi + c) = v;
+    }
+    LEAF_STAMP(14);
+}
+
 // batched 2-D copy  dst[b][r][c] = src[b][r][c]   (cols multiple of 2, 16-byte aligned)
 __global__ void copy2d_kernel(const double* __restrict__ src, int lds, long long ss,
                               double* __restrict__ dst, int ldd, long long sd, int rows, int cols)
@@ -812,7 +1074,8 @@ em_prep_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, int Ny, in
                const double* __restrict__ hyp, int hyp_ld, const double* __restrict__ alpha, long long sal,
                const double* __restrict__ z, const double* __restrict__ EMP,
                double* __restrict__ meanPart, int nblk,
-               double* __restrict__ E, double* __restrict__ F, double* __restrict__ W, double* __restrict__ IJ, int ldn)
+               double* __restrict__ E, double* __restrict__ F, double* __restrict__ W, double* __restrict__ IJ, int ldn,
+               double* __restrict__ LQ)
 {
     __shared__ double M[NXP * NXP];
     __shared__ double red[8];
@@ -837,6 +1100,9 @@ em_prep_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, int Ny, in
                 quad = fma(v[d], tacc, quad);
             }
         }
+        // log q_i = log c_a - 1/2 v^T (Sigma+Lambda_a)^-1 v: kept so the pair sums can form
+        // t Q_ij - q_i q_j = q_i q_j expm1(.) without cancellation (em_pair_kernel)
+        if (i < ldn) LQ[(long long)a * ldn + i] = (i < N) ? log(P[nn]) - 0.5 * quad : 0.0;
         double q = (i < N) ? P[nn] * exp(-0.5 * quad) * alpha[(long long)a * sal + i] : 0.0;
         q = warp_sum(q);
         if ((tid & 31) == 0) red[tid >> 5] = q;
@@ -883,25 +1149,34 @@ em_prep_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, int Ny, in
     F[(long long)p * ldn + i] = fj;
 }
 
-// sum_ij A_ij Q_ij for one pair; 64x64 tile per CTA, 4x4 per thread (:394-412)
+// sum_ij beta_a,i beta_b,j (t Q_ij - q_i q_j) for one pair; 64x64 tile per CTA, 4x4 per thread (:394-416).
+// The reference subtracts invK from beta beta^T on the diagonal pairs before the sum (:410-411),
+// which cancels 6-8 digits at cond(K) ~ 1e8-1e10 (negative variances on the car fixture, SURVEY
+// q18).  Here that term is evaluated separately and stably as tr(L^-1 Q L^-T) (em_q_kernel +
+// DMMA product + em_trdot_kernel): a trace of a positive semi-definite matrix, formed from the
+// Cholesky factor like var = sf2 - |L^-1 ks|^2 -- no explicit K^-1 anywhere.
+// mode 0: partial sums of beta_i beta_j q_ij into `part`; mode 1: q_ij itself into Qout (ld ldq,
+// zero outside N) for the pair's output a == b.
 __global__ void __launch_bounds__(256)
 em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
-               const double* __restrict__ alpha, long long sal, const double* __restrict__ KinvAll, int ldk, long long sKinv,
+               const double* __restrict__ alpha, long long sal,
                const double* __restrict__ E, const double* __restrict__ F, const double* __restrict__ W,
-               const double* __restrict__ IJ, int ldn, double* __restrict__ part)
+               const double* __restrict__ IJ, int ldn, const double* __restrict__ LQ, double* __restrict__ part,
+               int mode, int pair_q, double* __restrict__ Qout, int ldq)
 {
     extern __shared__ double sm[];
     double* Ws = sm; double* Js = sm + Nx * 64;
     __shared__ double red[8];
-    const int p = blockIdx.z, nn = Nx * Nx;
+    const int p = mode ? pair_q : blockIdx.z, nn = Nx * Nx;
     const double* P = EMP + (long long)Ny * (nn + 1) + (long long)p * (nn + 3);
     const int a = (int)P[nn + 1], b = (int)P[nn + 2];
+    const double logt = log(P[nn]);
     const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     for (int idx = tid; idx < Nx * 64; idx += 256) {
         const int d = idx >> 6, r = idx & 63;
-        Ws[idx] = W[((long long)p * Nx + d) * ldn + i0 + r];
-        Js[idx] = IJ[((long long)p * Nx + d) * ldn + j0 + r];
+        Ws[idx] = (i0 + r < ldn) ? W[((long long)p * Nx + d) * ldn + i0 + r] : 0.0;
+        Js[idx] = (j0 + r < ldn) ? IJ[((long long)p * Nx + d) * ldn + j0 + r] : 0.0;
     }
     __syncthreads();
     double acc[4][4];
@@ -920,7 +1195,6 @@ em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv[r], jv[c], acc[r][c]);
     }
-    const double* Kinv = KinvAll + (long long)a * sKinv;
     double s = 0.0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -928,14 +1202,18 @@ em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int j = j0 + tx + 16 * c;
-            if (i < N && j < N) {
-                const double q = exp(E[(long long)p * ldn + i] + F[(long long)p * ldn + j] + 2.0 * acc[r][c]);
-                double A = alpha[(long long)a * sal + i] * alpha[(long long)b * sal + j];
-                if (a == b) A -= Kinv[(long long)max(i, j) * ldk + min(i, j)];
-                s = fma(A, q, s);
+            const double lq = (i < N && j < N) ? E[(long long)p * ldn + i] + F[(long long)p * ldn + j] + 2.0 * acc[r][c] : 0.0;
+            if (mode) { if (i < ldq && j < ldq) Qout[(long long)i * ldq + j] = (i < N && j < N) ? exp(lq) : 0.0; }
+            else if (i < N && j < N) {
+                // beta_i beta_j (t Q_ij - q_i q_j) = (beta_i q_i)(beta_j q_j) expm1(log t + log Q_ij - log q_i - log q_j):
+                // the reference's  t beta^T Q beta - mean_a mean_b  (:412,416) term by term, before the sums cancel
+                const double la = LQ[(long long)a * ldn + i], lb = LQ[(long long)b * ldn + j];
+                const double wgt = (alpha[(long long)a * sal + i] * exp(la)) * (alpha[(long long)b * sal + j] * exp(lb));
+                s = fma(wgt, expm1(logt + lq - la - lb), s);
             }
         }
     }
+    if (mode) return;
     s = warp_sum(s);
     if ((tid & 31) == 0) red[tid >> 5] = s;
     __syncthreads();
@@ -946,11 +1224,39 @@ em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
     }
 }
 
+// tr(L^-1 Q L^-T) = sum_{k >= j} Wm[k][j] Li[k][j] with Wm = L^-1 Q (lower tiles): block partial sums,
+// grid (n/64 * (n/64+1)/2) lower 64x64 tiles
+__global__ void __launch_bounds__(256)
+em_trdot_kernel(const double* __restrict__ Wm, const double* __restrict__ Li, int ld, double* __restrict__ part)
+{
+    __shared__ double red[8];
+    const int tt = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * (double)tt + 1.0) - 1.0) * 0.5);
+    while (bi * (bi + 1) / 2 > tt) --bi;
+    while ((bi + 1) * (bi + 2) / 2 <= tt) ++bi;
+    const int bj = tt - bi * (bi + 1) / 2;
+    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+    double s = 0.0;
+    for (int r = ty; r < 64; r += 4) {
+        const int row = bi * 64 + r, col = bj * 64 + tx;
+        if (col <= row) s = fma(Wm[(long long)row * ld + col], Li[(long long)row * ld + col], s);
+    }
+    s = warp_sum(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double r = 0.0;
+        for (int w = 0; w < 8; ++w) r += red[w];
+        part[tt] = r;
+    }
+}
+
 // mean (Ny), cov (Ny,Ny): t_ab * sum (+ sf2 on the diagonal) - mean mean^T   (:412-416)
 __global__ void em_finalize_kernel(int Nx, int Ny, int npairs, const double* __restrict__ EMP,
                                    const double* __restrict__ hyp, int hyp_ld,
                                    const double* __restrict__ meanPart, int nblk,
                                    const double* __restrict__ part, int ntile2,
+                                   const double* __restrict__ trPart, int ntr,
                                    double* __restrict__ mean, double* __restrict__ var, double* __restrict__ cov)
 {
     __shared__ double mu[64];
@@ -967,9 +1273,14 @@ __global__ void em_finalize_kernel(int Nx, int Ny, int npairs, const double* __r
         const int a = (int)P[nn + 1], b = (int)P[nn + 2];
         double s = 0.0;
         for (int q = 0; q < ntile2; ++q) s += part[(long long)tid * ntile2 + q];
-        double c = P[nn] * s;
-        if (a == b) { const double sf = hyp[(long long)a * hyp_ld + Nx]; c += sf * sf; }
-        c -= mu[a] * mu[b];
+        double c = s;       // = t beta_a^T Q beta_b - mean_a mean_b, summed term by term without the cancellation
+        if (a == b) {
+            // + expected variance  sf2 - t tr(K^-1 Q_aa)  from the Cholesky-based trace (two positive numbers)
+            double tr = 0.0;
+            for (int q = 0; q < ntr; ++q) tr += trPart[(long long)a * ntr + q];
+            const double sf = hyp[(long long)a * hyp_ld + Nx];
+            c += sf * sf - P[nn] * tr;
+        }
         if (cov) { cov[a * Ny + b] = c; cov[b * Ny + a] = c; }
         if (a == b && var) var[a] = c;
     }

@@ -71,6 +71,7 @@ struct PredictParams {
 
 // ---- stage 5: assemble mean (H,Ny), var (H,Ny), J (H,Ny,Nx) and the covariance for test point h:
 // 'ME' diag(var) (gp_functions.py:142); 'TA' diag(var) + J Sigma J^T (build_TA_cov, :167-171).
+template <bool WARP>
 __device__ __forceinline__ void assemble_point(const AssembleArgs& A, int h, double* sh, int tid, int nth)
 {
     const int Ny = A.Ny, Nx = A.Nx, H = A.H;
@@ -88,7 +89,7 @@ __device__ __forceinline__ void assemble_point(const AssembleArgs& A, int h, dou
         if (A.var) A.var[(long long)h * Ny + a] = v;
         vh[a] = v;
     }
-    __syncthreads();
+    if (WARP) __syncwarp(); else __syncthreads();
     if (A.cov) {
         if (A.method_ta) {
             const double* Sg = A.Sigma + (A.sigma_per_point ? (long long)h * Nx * Nx : 0);
@@ -98,7 +99,7 @@ __device__ __forceinline__ void assemble_point(const AssembleArgs& A, int h, dou
                 for (int d = 0; d < Nx; ++d) s = fma(Jh[a * Nx + d], Sg[d * Nx + e], s);
                 JS[idx] = s;
             }
-            __syncthreads();
+            if (WARP) __syncwarp(); else __syncthreads();
         }
         for (int idx = tid; idx < Ny * Ny; idx += nth) {
             const int a = idx / Ny, b = idx % Ny;
@@ -111,7 +112,7 @@ __device__ __forceinline__ void assemble_point(const AssembleArgs& A, int h, dou
             A.cov[((long long)h * Ny + a) * Ny + b] = s;
         }
     }
-    __syncthreads();
+    if (WARP) __syncwarp(); else __syncthreads();
 }
 
 // peer mode: acquire every source rank's flag for this step; false = a rank never showed up
@@ -145,7 +146,7 @@ assemble_kernel(const AssembleArgs A)
     extern __shared__ double sh[];          // Jh[Ny][Nx], JS[Ny][Nx], varh[Ny]
     __shared__ int ok;
     if (!peer_acquire(A, threadIdx.x, &ok)) return;
-    for (int h = blockIdx.x; h < A.H; h += gridDim.x) assemble_point(A, h, sh, threadIdx.x, blockDim.x);
+    for (int h = blockIdx.x; h < A.H; h += gridDim.x) assemble_point<false>(A, h, sh, threadIdx.x, blockDim.x);
 }
 
 struct PskIter { int a, jt, s, ks; };
@@ -220,8 +221,11 @@ __device__ __forceinline__ void psk_step_tail(const PredictParams& p, double* sh
     }
     if (p.do_assemble) {
         __threadfence();
-        if (peer_acquire(p.as, tid, s_ok))
-            for (int h = 0; h < p.as.H; ++h) assemble_point(p.as, h, sh, tid, nth);
+        // one warp per test point (a single CTA is assembling: 8 points in flight instead of 1)
+        if (peer_acquire(p.as, tid, s_ok)) {
+            double* shw = sh + (tid >> 5) * (2 * p.as.Ny * p.as.Nx + p.as.Ny);
+            for (int h = tid >> 5; h < p.as.H; h += nth >> 5) assemble_point<true>(p.as, h, shw, tid & 31, 32);
+        }
     }
 }
 

@@ -442,6 +442,74 @@ def gp_exact_moment(invK, X, Y, hyper, inputmean, inputcov, extended=False):
     return mean, covariance
 
 
+def gp_exact_moment_mp(X, Y, hyper, inputmean, inputcov, dps=40):
+    """The formula of ``gp_exact_moment`` (``gp_functions.py:344-418``) evaluated in ``dps``-digit
+    arithmetic (mpmath) FROM (X, Y, hyper): K, K^-1, beta = K^-1 y and every N x N sum are exact to
+    ~dps digits, so this is what the reference's expression means mathematically -- the yardstick
+    for any fp64 evaluation (the fp64 restatement above loses 4-8 digits to the beta beta^T - invK
+    cancellation; the GPU engine evaluates an algebraically identical, better conditioned form).
+    Slow (pure Python): used offline by ``oracle/make_golden_em.py``.  Returns mean:(Ny,), cov:(Ny,Ny)."""
+    import mpmath as mp
+    mp.mp.dps = dps
+    X = np.asarray(X, dtype=np.float64); Y = np.asarray(Y, dtype=np.float64)
+    hyper = np.atleast_2d(np.asarray(hyper, dtype=np.float64))
+    mu = [mp.mpf(float(t)) for t in np.asarray(inputmean, dtype=np.float64).reshape(-1)]
+    N, Nx = X.shape
+    Ny = hyper.shape[0]
+    S = mp.matrix([[mp.mpf(float(inputcov[i, j])) for j in range(Nx)] for i in range(Nx)])
+    Xm = [[mp.mpf(float(X[i, d])) for d in range(Nx)] for i in range(N)]
+    v = [[Xm[i][d] - mu[d] for d in range(Nx)] for i in range(N)]
+    eye = mp.eye(Nx)
+    ell2 = [[mp.mpf(float(hyper[a, d])) ** 2 for d in range(Nx)] for a in range(Ny)]
+    sf2 = [mp.mpf(float(hyper[a, Nx])) ** 2 for a in range(Ny)]
+    sn2 = [mp.mpf(float(hyper[a, Nx + 1])) ** 2 for a in range(Ny)]
+    invK = []; beta = []; q = []; logk = []
+    for a in range(Ny):
+        K = mp.matrix(N, N)
+        for i in range(N):
+            for j in range(i + 1):
+                d2 = sum((Xm[i][d] - Xm[j][d]) ** 2 / ell2[a][d] for d in range(Nx))
+                K[i, j] = K[j, i] = sf2[a] * mp.exp(-d2 / 2)
+            K[i, i] += sn2[a]
+        Ki = K ** -1
+        invK.append(Ki)
+        beta.append(Ki * mp.matrix([mp.mpf(float(Y[i, a])) for i in range(N)]))
+        R = S + mp.diag(ell2[a])                                         # :383
+        iR = R ** -1
+        c = sf2[a] / mp.sqrt(mp.det(R)) * mp.sqrt(mp.fprod(ell2[a]))   # :386-387 (prod ell = sqrt(prod ell^2))
+        qa = []
+        for i in range(N):
+            vi = mp.matrix(v[i])
+            qa.append(c * mp.exp(-(vi.T * iR * vi)[0] / 2))              # :385,388
+        q.append(qa)
+        logk.append([mp.log(sf2[a]) - sum(v[i][d] ** 2 / ell2[a][d] for d in range(Nx)) / 2 for i in range(N)])  # :389-391
+    mean = [sum(q[a][i] * beta[a][i] for i in range(N)) for a in range(Ny)]
+    cov = np.zeros((Ny, Ny))
+    for a in range(Ny):
+        ii = [mp.matrix([v[i][d] / ell2[a][d] for d in range(Nx)]) for i in range(N)]
+        for b in range(a + 1):
+            ij = [mp.matrix([v[i][d] / ell2[b][d] for d in range(Nx)]) for i in range(N)]
+            R = S * mp.diag([1 / ell2[a][d] + 1 / ell2[b][d] for d in range(Nx)]) + eye     # :396-397
+            t = 1 / mp.sqrt(mp.det(R))
+            Qm = (R ** -1) * S / 2                                      # :402
+            Qi = [Qm.T * ii[i] for i in range(N)]                       # maha(ii, -ij, Qm) = (ii+ij)^T Qm (ii+ij)
+            Qj = [Qm * ij[j] for j in range(N)]
+            dii = [(ii[i].T * Qm * ii[i])[0] for i in range(N)]
+            djj = [(ij[j].T * Qm * ij[j])[0] for j in range(N)]
+            acc = mp.mpf(0)
+            for i in range(N):
+                for j in range(N):
+                    mh = dii[i] + djj[j] + (ii[i].T * Qj[j])[0] + (Qi[i].T * ij[j])[0]
+                    Aij = beta[a][i] * beta[b][j] - (invK[a][i, j] if a == b else 0)      # :409-411
+                    acc += Aij * mp.exp(logk[a][i] + logk[b][j] + mh)
+            cab = t * acc
+            if a == b:
+                cab += sf2[a]                                           # :415
+            cab -= mean[a] * mean[b]                                    # :416
+            cov[a, b] = cov[b, a] = float(cab)
+    return np.array([float(m) for m in mean]), cov
+
+
 # ----------------------------------------------------------------------------
 # a11/a12/a13  predict wrapper, linearisation, scalers
 # ----------------------------------------------------------------------------
