@@ -37,7 +37,8 @@ WORKLOADS = {
     'c2': dict(N=1000, Nx=8, Ny=6, H=30, cfg=2, name='C2: N=1000 Nx=8 Ny=6 H=30 TA'),
 }
 METRIC = 'GP predictions/sec (N train x horizon test, fp64)'
-PREDICT_KERNEL_NAME = 'gemm_dmma_tmap_kernel<BM,128,1,8,4,2> (v = Linv ks: DMMA fed by TMA tensor maps, split-K, longest-first)'
+PREDICT_KERNEL_NAME = ('predict_streamk_kernel<BM> (v = Linv ks: persistent stream-K DMMA product fed by TMA tensor maps, '
+                       'fused squared-norm reduction / finalize / peer store / covariance assembly)')
 
 
 def make_workload(N, Nx, Ny, cfg, H):
@@ -381,15 +382,15 @@ def main():
     if sec:
         Np = (N + 127) // 128 * 128
         n1 = (Np // 128 // 2) * 128; n2 = Np - n1
-        syrk_flops = float(n2) * (n2 + 128) * n1              # lower tiles incl. the diagonal ones, 2 flops/MAC
+        syrk_flops = float(n2) * (n2 + 1) * n1                # lower triangle incl. the diagonal, 2 flops per multiply-add
         secondary = {
             'kbuild_full': {'ms': sec['kbuild_full_ms'], 'gbs': 8.0 * Np * Np / sec['kbuild_full_ms'] / 1e6,
                             'frac': 8.0 * Np * Np / sec['kbuild_full_ms'] / 1e6 / hbm_peak, 'bound': 'hbm',
                             'algorithmic_bytes': 8.0 * Np * Np, 'traffic': tj.get('kbuild_full_N16384_bytes') if N == 16384 else None,
                             'peak_source': hbm_src},
-            'kbuild_lower': {'ms': sec['kbuild_lower_ms'], 'gbs': 4.0 * Np * (Np + 128) / sec['kbuild_lower_ms'] / 1e6,
-                             'frac': 4.0 * Np * (Np + 128) / sec['kbuild_lower_ms'] / 1e6 / hbm_peak, 'bound': 'hbm',
-                             'algorithmic_bytes': 4.0 * Np * (Np + 128)},
+            'kbuild_lower': {'ms': sec['kbuild_lower_ms'], 'gbs': 4.0 * Np * (Np + 1) / sec['kbuild_lower_ms'] / 1e6,
+                             'frac': 4.0 * Np * (Np + 1) / sec['kbuild_lower_ms'] / 1e6 / hbm_peak, 'bound': 'hbm',
+                             'algorithmic_bytes': 4.0 * Np * (Np + 1)},
             'syrk_trailing_update': {'ms': sec['syrk_ms'], 'tflops': syrk_flops / sec['syrk_ms'] / 1e9,
                                      'frac': syrk_flops / sec['syrk_ms'] / 1e9 / dgemm_tf, 'bound': 'tensor',
                                      'shape': 'C(%d x %d lower) -= P P^T, K=%d' % (n2, n2, n1),
@@ -398,6 +399,20 @@ def main():
                                       'frac': (2.0 / 3.0) * float(Np) ** 3 / sec['factorize_ms'] / 1e9 / dgemm_tf, 'bound': 'tensor',
                                       'note': 'K build + potrf + explicit L^-1 of one output, 2N^3/3 flops'},
         }
+        if rank == 0 and world == 1:
+            # sequential H=1 predicts (examples/van_der_pol.py:34-38: 2000 gp.predict calls in a Python loop): the
+            # HBM-bound regime -- every step streams the lower triangle of every output's L^-1 once
+            z1 = np.ascontiguousarray(w['Z'][:1])
+            for _ in range(3):
+                eng.predict(z1, None, L.METHOD_ME, want_jac=False)
+            t1 = time.perf_counter(); n1 = 50
+            for _ in range(n1):
+                eng.predict(z1, None, L.METHOD_ME, want_jac=False)
+            ms1 = (time.perf_counter() - t1) / n1 * 1e3
+            secondary['sequential_h1'] = {'ms_per_call_e2e': ms1, 'calls_per_s': 1e3 / ms1, 'bound': 'hbm',
+                                          'algorithmic_bytes': n * 4.0 * Np * (Np + 1), 'gbs': n * 4.0 * Np * (Np + 1) / ms1 / 1e6,
+                                          'frac': n * 4.0 * Np * (Np + 1) / ms1 / 1e6 / hbm_peak,
+                                          'note': 'host C-ABI call per step (H2D + 2 launches + D2H + sync inside), method ME, N=%d, %d outputs' % (N, n)}
         if rank == 0 and world == 1 and os.environ.get('GPMPC_BENCH_NLML', '1') == '1':
             # BASELINE config C4: NLML + analytic gradient at N=8192, Nx=8 (one output) through the C ABI
             w4 = make_workload(8192, 8, 1, 4, 1)
@@ -467,7 +482,9 @@ def main():
                            'setup_s': t_setup},
                 'clocks': clocks,
                 'e2e': {'value': e2e_val, 'unit': 'predictions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-                'gpu_launches': args.steps * (4 * ((H + 63) // 64) + 1),
+                # per 64-point chunk: ks_mean_jac_kernel + predict_streamk_kernel (the latter also reduces, finalizes,
+                # stores to the peers and assembles); a separate assemble_kernel only for H > 64 or the NCCL fallback
+                'gpu_launches': args.steps * (2 * ((H + 63) // 64) + (1 if (H > 64 or (world > 1 and not peer_mode)) else 0)),
                 'roofline': roofline, 'roofline_secondary': secondary, 'parity_vs_oracle': parity, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     eng.close()

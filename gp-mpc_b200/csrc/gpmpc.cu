@@ -276,10 +276,10 @@ static int launch_kbuild(gpmpc_handle_t h, const double* dHyp, const double* dJi
 {
     static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
     const int KD = (h->Nx + 3) & ~3, S = ((KD >> 2) & 1) ? KD : KD + 4;
-    const int smem = (2 * KB2_TILE * S + 2 * KB2_TILE + 16) * 8;
+    const int smem = (2 * KB2_TILE * S + 2 * KB2_TILE + 256) * 8;
     if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
         CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (2 * KB2_TILE * 36 + 2 * KB2_TILE + 16) * 8));
+                                      (2 * KB2_TILE * 36 + 2 * KB2_TILE + 256) * 8));
         conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
     }
     const int T = h->Npad / KB2_TILE;

@@ -12,8 +12,8 @@
 //   With u_i = sqrt(log2 e) (x_i - mu)/ell and q_i = -1/2 |u_i|^2 + 1/2 log2 sf2,
 //       log2 k(x_i, x_j) = q_i + q_j + u_i . u_j            (= log2 sf2 - log2(e)/2 |xs_i - xs_j|^2)
 //   so the O(N^2 Nx) part is a rank-Nx product done with DMMA m8n8k4 (tensor pipe), leaving the
-//   fp64 pipe only ~14 instructions per pair (two adds, clamp, a 16-entry-table exp2 with a
-//   degree-7 polynomial).  ncu on the first (direct-difference, libm exp) kernel showed the fp64 pipe 48 % busy and DRAM 41 %:
+//   fp64 pipe only ~12 instructions per pair (two adds, clamp, a 256-entry-table exp2 with a
+//   degree-4 polynomial).  ncu on the first (direct-difference, libm exp) kernel showed the fp64 pipe 48 % busy and DRAM 41 %:
 //   the two pipes now overlap and the kernel becomes write-bandwidth bound.
 //   The kernel is translation invariant, so inputs are centred on the column means mu: the
 //   expansion's cancellation error is eps*|u|^2 with |u| measured from the data centre
@@ -23,32 +23,90 @@
 //   mirrored tile (each exp2 serves two outputs).  q_i + q_j and the k-ordered dot product are
 //   commutative, so K is bitwise symmetric, including inside diagonal tiles.
 // ---------------------------------------------------------------------------------------
-__constant__ double c_exp2_tab[16] = {
-    1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721,
-    1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951,
-    1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429,
-    1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+// 2^(n/256), n = 0..255, correctly rounded (generated with 40-digit arithmetic)
+__constant__ double c_exp2_tab256[256] = {
+    1, 1.0027112750502025, 1.0054299011128027, 1.0081558981184175,
+    1.0108892860517005, 1.0136300849514894, 1.0163783149109531, 1.0191339960777379,
+    1.0218971486541166, 1.0246677928971357, 1.0274459491187637, 1.030231637686041,
+    1.0330248790212284, 1.0358256936019572, 1.0386341019613787, 1.0414501246883161,
+    1.0442737824274138, 1.0471050958792898, 1.0499440858006872, 1.0527907730046264,
+    1.0556451783605572, 1.0585073227945128, 1.0613772272892621, 1.0642549128844645,
+    1.0671404006768237, 1.0700337118202419, 1.0729348675259756, 1.075843889062791,
+    1.0787607977571199, 1.0816856149932152, 1.0846183622133092, 1.0875590609177697,
+    1.0905077326652577, 1.0934643990728858, 1.0964290818163769, 1.0994018026302219,
+    1.1023825833078409, 1.1053714457017412, 1.1083684117236787, 1.1113735033448175,
+    1.1143867425958924, 1.1174081515673693, 1.1204377524096067, 1.1234755673330199,
+    1.1265216186082418, 1.1295759285662881, 1.1326385195987192, 1.1357094141578055,
+    1.1387886347566916, 1.1418762039695616, 1.1449721444318042, 1.1480764788401789,
+    1.1511892299529827, 1.1543104205902159, 1.1574400736337511, 1.1605782120274988,
+    1.1637248587775775, 1.1668800369524817, 1.1700437696832502, 1.1732160801636373,
+    1.1763969916502812, 1.1795865274628758, 1.182784710984341, 1.1859915656609938,
+    1.189207115002721, 1.1924313825831512, 1.1956643920398273, 1.1989061670743806,
+    1.2021567314527031, 1.2054161090051239, 1.2086843236265816, 1.2119613992768012,
+    1.215247359980469, 1.2185422298274085, 1.2218460329727576, 1.2251587936371455,
+    1.22848053610687, 1.2318112847340759, 1.2351510639369334, 1.2384998981998165,
+    1.241857812073484, 1.245224830175258, 1.2486009771892048, 1.2519862778663162,
+    1.2553807570246911, 1.2587844395497165, 1.2621973503942507, 1.2656195145788063,
+    1.2690509571917332, 1.2724917033894028, 1.275941778396392, 1.2794012075056693,
+    1.2828700160787783, 1.2863482295460256, 1.2898358734066657, 1.2933329732290895,
+    1.2968395546510096, 1.3003556433796506, 1.3038812651919358, 1.3074164459346773,
+    1.3109612115247644, 1.3145155879493546, 1.318079601266064, 1.3216532776031575,
+    1.3252366431597413, 1.3288297242059544, 1.3324325470831615, 1.3360451382041458,
+    1.3396675240533029, 1.3432997311868353, 1.3469417862329458, 1.3505937158920345,
+    1.3542555469368927, 1.3579273062129011, 1.3616090206382248, 1.3653007172040119,
+    1.3690024229745905, 1.3727141650876684, 1.3764359707545302, 1.380167867260238,
+    1.383909881963832, 1.3876620422985291, 1.3914243757719262, 1.3951969099662003,
+    1.3989796725383112, 1.4027726912202048, 1.4065759938190154, 1.4103896082172707,
+    1.4142135623730951, 1.4180478843204152, 1.4218926021691656, 1.4257477441054942,
+    1.42961333839197, 1.4334894133677889, 1.4373759974489824, 1.4412731191286257,
+    1.4451808069770467, 1.449099089642035, 1.4530279958490526, 1.4569675544014438,
+    1.460917794180647, 1.4648787441464057, 1.4688504333369818, 1.4728328908693675,
+    1.4768261459394993, 1.4808302278224719, 1.4848451658727524, 1.488870989524397,
+    1.4929077282912648, 1.4969554117672355, 1.5010140696264256, 1.5050837316234065,
+    1.5091644275934228, 1.5132561874526098, 1.5173590411982147, 1.5214730189088146,
+    1.5255981507445384, 1.529734466947287, 1.5338819978409559, 1.5380407738316568,
+    1.5422108254079407, 1.5463921831410214, 1.550584877685, 1.5547889397770887,
+    1.5590044002378369, 1.5632312899713576, 1.567469639965553, 1.5717194812923414,
+    1.5759808451078865, 1.5802537626528246, 1.5845382652524937, 1.588834384317164,
+    1.593142151342267, 1.5974615979086271, 1.6017927556826934, 1.606135656416771,
+    1.6104903319492543, 1.6148568142048607, 1.6192351351948637, 1.6236253270173289,
+    1.6280274218573478, 1.632441451987275, 1.6368674497669644, 1.6413054476440063,
+    1.6457554781539649, 1.6502175739206177, 1.6546917676561943, 1.6591780921616162,
+    1.6636765803267364, 1.6681872651305825, 1.6727101796415966, 1.6772453570178785,
+    1.681792830507429, 1.6863526334483934, 1.6909247992693053, 1.6955093614893326,
+    1.7001063537185235, 1.7047158096580513, 1.7093377631004629, 1.713972247929926,
+    1.7186192981224779, 1.723278947746274, 1.7279512309618377, 1.7326361820223111,
+    1.7373338352737062, 1.7420442251551564, 1.746767386199169, 1.7515033530318782,
+    1.7562521603732995, 1.7610138430375839, 1.7657884359332727, 1.7705759740635547,
+    1.7753764925265212, 1.7801900265154245, 1.785016611318935, 1.789856282321401,
+    1.7947090750031072, 1.7995750249405351, 1.8044541678066239, 1.809346539371032,
+    1.8142521755003989, 1.8191711121586085, 1.8241033854070534, 1.8290490314048973,
+    1.8340080864093424, 1.8389805867758937, 1.843966568958626, 1.8489660695104508,
+    1.8539791250833855, 1.8590057724288205, 1.864046048397789, 1.8690999899412386,
+    1.8741676341103, 1.8792490180565602, 1.8843441790323345, 1.8894531543909392,
+    1.8945759815869656, 1.8997126981765553, 1.9048633418176741, 1.9100279502703899,
+    1.9152065613971474, 1.9203992131630474, 1.925605943636125, 1.9308267909876271,
+    1.9360617934922943, 1.9413109895286405, 1.9465744175792332, 1.9518521162309783,
+    1.9571441241754002, 1.9624504802089273, 1.9677712232331759, 1.9731063922552343,
+    1.9784560263879509, 1.9838201648502194, 1.9891988469672663, 1.9945921121709402};
 
-// 2^t for t <= ~1000; results below 2^-1020 flush to zero.  ~2 ulp.
-__device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ T16)
+// 2^t for -1020 <= t <= ~1000 (the caller clamps): 256-entry table + degree-4 polynomial on
+// |f| <= 1/512 (truncation 3.8e-17), ~1.7 ulp.  Per value: 2 (rint by magic constant) + 1 (f) +
+// 4 (Horner) + table load + multiply + exponent insert -- the r1 kernel (16-entry table, degree 7)
+// was bound by issue slots (67 % active), not by HBM.
+__device__ __forceinline__ double exp2_t256(double t, const double* __restrict__ T256)
 {
-    t = fmax(t, -1080.0);
-    const double SH = 6755399441055744.0;            // 1.5 * 2^52: rint(16 t) lands in the low word
-    const double s = fma(t, 16.0, SH);
+    const double SH = 6755399441055744.0;            // 1.5 * 2^52: rint(256 t) lands in the low word
+    const double s = fma(t, 256.0, SH);
     const int n = __double2loint(s);
-    const double f = fma(s - SH, -0.0625, t);        // |f| <= 1/32, exact
-    double p = 1.5252733804059838e-05;               // (ln 2)^k / k!, k = 7..1
-    p = fma(p, f, 0.00015403530393381606);
-    p = fma(p, f, 0.0013333558146428441);
-    p = fma(p, f, 0.009618129107628477);
-    p = fma(p, f, 0.055504108664821576);
-    p = fma(p, f, 0.2402265069591007);
+    const double f = fma(s - SH, -0.00390625, t);    // |f| <= 1/512, exact
+    double p = 0.009618129107628477;                 // (ln 2)^k / k!, k = 4..1
+    p = fma(p, f, 0.05550410866482158);
+    p = fma(p, f, 0.24022650695910072);
     p = fma(p, f, 0.6931471805599453);
     p = fma(p, f, 1.0);
-    p *= T16[n & 15];
-    const int e = n >> 4;
-    if (e < -1020) return 0.0;
-    return __hiloint2double(__double2hiint(p) + (e << 20), __double2loint(p));
+    p *= T256[n & 255];
+    return __hiloint2double(__double2hiint(p) + ((n >> 8) << 20), __double2loint(p));
 }
 
 #define KB2_TILE 128
@@ -64,7 +122,7 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
     double* Uj = Ui + KB2_TILE * S;                       // [128][S]
     double* qi = Uj + KB2_TILE * S;                       // [128]
     double* qj = qi + KB2_TILE;                           // [128]
-    double* T16 = qj + KB2_TILE;                          // [16]
+    double* T256 = qj + KB2_TILE;                         // [256]
 
     const int a = blockIdx.z;
     const double* hp = hyp + (long long)a * hyp_ld;
@@ -78,18 +136,24 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
     const double sf2 = hp[Nx] * hp[Nx];
     const double l2sf2 = log2(sf2);
 
+    __shared__ double sc[36], mus[36];                    // sqrt(log2 e) / ell_d and the column means: one division per dimension per CTA
+    if (tid < S) {
+        sc[tid] = (tid < Nx) ? 1.2011224087864498 / hp[tid] : 0.0;
+        mus[tid] = (tid < Nx) ? mu[tid] : 0.0;
+    }
+    T256[tid] = c_exp2_tab256[tid];
+    __syncthreads();
     {   // scaled, centred coordinates of the 128 row points (tid < 128) / column points
         const int p = (tid < KB2_TILE) ? i0 + tid : j0 + tid - KB2_TILE;
         double* U = (tid < KB2_TILE) ? Ui + tid * S : Uj + (tid - KB2_TILE) * S;
         double nrm = 0.0;
         for (int d = 0; d < S; ++d) {
             double u = 0.0;
-            if (d < Nx) u = (XT[(long long)d * ldx + p] - mu[d]) * (1.2011224087864498 / hp[d]);
+            if (d < Nx) u = (XT[(long long)d * ldx + p] - mus[d]) * sc[d];
             U[d] = u;
             nrm = fma(u, u, nrm);
         }
         ((tid < KB2_TILE) ? qi : qj)[tid & (KB2_TILE - 1)] = fma(-0.5, nrm, 0.5 * l2sf2);
-        if (tid < 16) T16[tid] = c_exp2_tab[tid];
     }
     __syncthreads();
 
@@ -124,8 +188,8 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
             for (int q = 0; q < 4; ++q) {
                 const int cl0 = ng * 32 + q * 8;          // + 2t folded into the base pointers
                 const double2 qc = *reinterpret_cast<const double2*>(qj + cl0 + 2 * t);
-                double v0 = exp2_tab(fmin((qr + qc.x) + acc[q][0], l2sf2), T16);
-                double v1 = exp2_tab(fmin((qr + qc.y) + acc[q][1], l2sf2), T16);
+                double v0 = exp2_t256(fmax(fmin((qr + qc.x) + acc[q][0], l2sf2), -1020.0), T256);
+                double v1 = exp2_t256(fmax(fmin((qr + qc.y) + acc[q][1], l2sf2), -1020.0), T256);
                 if (special) {
                     const int col = j0 + cl0 + 2 * t;
                     if (row == col) v0 += dg;

@@ -62,11 +62,13 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
     jac_mode = 'analytic'
     fixed_bounds = False
     fit_mean = False
+    parallel_fits = True
     if optimizer_opts is not None:
         optimizer_opts = dict(optimizer_opts)
         jac_mode = optimizer_opts.pop('jac', jac_mode)
         fixed_bounds = bool(optimizer_opts.pop('fixed_bounds', False))
         fit_mean = bool(optimizer_opts.pop('fit_mean', False)) and h_m > 0
+        parallel_fits = bool(optimizer_opts.pop('parallel_fits', True))
         options.update(optimizer_opts)
     if jac_mode not in ('analytic', 'fd'):
         raise ValueError("optimizer_opts['jac'] must be 'analytic' or 'fd'")
@@ -76,11 +78,12 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
         print('# Optimizing hyperparameters (N=%d)' % N)
         print('----------------------------------------')
     rows = np.zeros((engine.out_count, Nx + 2 + h_m))
-    for k, a in enumerate(engine.local_outputs):
+
+    def fit_one(eng, a):
+        """SLSQP for output a on `eng` (any engine that owns a); returns (hyper row, seconds)."""
         bounds, init = bounds_and_init(X, Y[:, a], fixed_bounds)
         if hyper_init is not None:
             init = np.asarray(hyper_init, dtype=np.float64)[a, :Nx + 2].copy()
-
         if fit_mean:
             from ._lib import GET_ALPHA_NLML
             Phi = mean_design(X, meanFunc)
@@ -89,27 +92,59 @@ def train_gp_b200(engine, X, Y, meanFunc='zero', hyper_init=None, multistart=1,
                                    else np.asarray(hyper_init, dtype=np.float64)[a, Nx + 2:Nx + 2 + h_m]])
             init = np.clip(init, bounds[:, 0], bounds[:, 1])
 
-        def fun(theta, a=a):
+        def fun(theta):
             if fit_mean:
-                engine.set_y(a, Y[:, a] - Phi @ theta[Nx + 2:])
+                eng.set_y(a, Y[:, a] - Phi @ theta[Nx + 2:])
                 if jac_mode != 'analytic':
-                    return engine.nlml(a, theta[:Nx + 2], grad=False)
-                nll, g = engine.nlml(a, theta[:Nx + 2], grad=True)
-                return nll, np.concatenate([g, -Phi.T @ engine.get(GET_ALPHA_NLML, a)])
+                    return eng.nlml(a, theta[:Nx + 2], grad=False)
+                nll, g = eng.nlml(a, theta[:Nx + 2], grad=True)
+                return nll, np.concatenate([g, -Phi.T @ eng.get(GET_ALPHA_NLML, a)])
             if jac_mode == 'analytic':
-                return engine.nlml(a, theta, grad=True)
-            return engine.nlml(a, theta, grad=False)
+                return eng.nlml(a, theta, grad=True)
+            return eng.nlml(a, theta, grad=False)
 
         # multistart re-runs from the SAME init (optimize.py:462-469, q8): identical results,
         # so one run decides
         t0 = time.time()
         res = minimize(fun, init, method='SLSQP', jac=(jac_mode == 'analytic'), options=options,
                        bounds=bounds, tol=1e-12)
-        if verbose:
-            print("* State %d:  %f s" % (a, time.time() - t0))
-        rows[k, :len(res.x)] = res.x
         if fit_mean:
-            engine.set_y(a, Y[:, a])
+            eng.set_y(a, Y[:, a])
+        return res.x, time.time() - t0
+
+    outs = list(engine.local_outputs)
+    workers = None
+    if parallel_fits and len(outs) > 1 and hasattr(engine, 'device'):
+        # The per-output fits are independent (optimize.py:433 loops over them) and each NLML evaluation
+        # is latency-bound below N ~ 8192 (its potrf recursion leaves most SMs idle): run them
+        # concurrently, one scratch engine (own CUDA streams) and one host thread per output.  ctypes
+        # releases the GIL inside the library calls.  Falls back to the sequential loop when the
+        # scratch engines do not fit in device memory.
+        try:
+            workers = []
+            for a in outs:
+                w = type(engine)(engine.N, Nx, engine.Ny, a, 1, engine.device)
+                w.set_data(X, Y)
+                workers.append(w)
+        except Exception:
+            for w in workers or []:
+                w.close()
+            workers = None
+    if workers:
+        from concurrent.futures import ThreadPoolExecutor
+        try:
+            with ThreadPoolExecutor(max_workers=len(outs)) as ex:
+                futs = [ex.submit(fit_one, w, a) for w, a in zip(workers, outs)]
+                results = [f.result() for f in futs]
+        finally:
+            for w in workers:
+                w.close()
+    else:
+        results = [fit_one(engine, a) for a in outs]
+    for k, (a, (x, secs)) in enumerate(zip(outs, results)):
+        if verbose:
+            print("* State %d:  %f s" % (a, secs))
+        rows[k, :len(x)] = x
     if verbose:
         print('----------------------------------------')
     return rows
