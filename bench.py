@@ -127,6 +127,17 @@ def cpu_predict_port(orc, X, hyper_a, alpha_a, L_a, Z):
     return mean, var, J
 
 
+def all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs (reference arm, oracle parity) are meant to use every
+    host core, so lift the BLAS/OpenMP limits at run time."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def run_reference(args, wl, rank):
     """--impl reference: the reference's own CPU path for this metric (oracle port; the
     reference is pure Python on numpy/CasADi, CasADi is not installable here) on all host
@@ -138,6 +149,8 @@ def run_reference(args, wl, rank):
     if rank != 0:
         return
     from oracle import gp_oracle as orc
+    _limits = all_host_threads()
+    _limits.__enter__()
     N, Nx, Ny, H = wl['N'], wl['Nx'], wl['Ny'], wl['H']
     w = make_workload(N, Nx, Ny, wl['cfg'], H)
     try:
@@ -437,6 +450,8 @@ def main():
     parity = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import gp_oracle as orc
+        _limits = all_host_threads()
+        _limits.__enter__()
         outs = sorted({0, Ny - 1})          # rank 0's own first output and the last rank's last output
         ref = {}
         t_fac = 0.0

@@ -592,6 +592,7 @@ extern "C" int gpmpc_factorize(gpmpc_handle_t h, double jitter, int* info)
     if (!h) return GPMPC_ERR_ARG;
     if (!h->has_data || !h->has_hyper) { set_error(h, "gpmpc_factorize: set_data and set_hyper first"); return GPMPC_ERR_STATE; }
     CUDA_TRY(cudaSetDevice(h->device));
+    NvtxRange nvtx_r("gpmpc.factorize");
     const int nl = h->nloc;
     CUDA_TRY(cudaMemsetAsync(h->dJit, 0, nl * sizeof(double), h->st));
     CUDA_TRY(cudaMemsetAsync(h->dInfo, 0, nl * sizeof(int), h->st));
@@ -663,6 +664,7 @@ extern "C" int gpmpc_nlml(gpmpc_handle_t h, int a, const double* theta, double* 
     const int m = h->Nx + 2;
     for (int d = 0; d < h->Nx; ++d) if (theta[d] == 0.0) { set_error(h, "gpmpc_nlml: zero length scale"); return GPMPC_ERR_ARG; }
     h->factorized = false;
+    NvtxRange nvtx_r("gpmpc.nlml");
     CUDA_TRY(cudaMemcpyAsync(h->dHypTmp, theta, m * 8, cudaMemcpyHostToDevice, h->st));
     int used = 0;
     int rc = factor_one(h, al, h->dHypTmp, 1e-8, &used);     // optimize.py:345-350
@@ -824,12 +826,13 @@ static cudaError_t psk_launch(int bm, const PredictParams& p, const double* A, l
     }
 }
 
-// persistent grid: 2 CTAs per SM, but never fewer than 32 k-steps per CTA
+// persistent grid: 2 CTAs per SM, but never fewer than 12 k-steps per CTA (small N: a CTA's fixed cost -- barrier
+// init, descriptor fetch, pipeline fill -- is worth about 8 steps)
 static int psk_grid(gpmpc_handle_t h, long long G)
 {
     int ctas = h->opt_predict_ctas > 0 ? h->opt_predict_ctas : h->psk_ctas;
     ctas = std::min(ctas, PSK_MAX_CTAS);
-    const long long by_work = std::max(1LL, G / 32);
+    const long long by_work = std::max(1LL, G / 12);
     return (int)std::min<long long>(ctas, h->opt_predict_ctas > 0 ? G : by_work);
 }
 
@@ -1059,6 +1062,7 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
                       double* mean, double* var, double* cov)
 {
     const int Nx = h->Nx, Ny = h->Ny, nn = Nx * Nx, np = h->Npad;
+    NvtxRange nvtx_r("gpmpc.predict_em");
     if (h->nloc != Ny) { set_error(h, "EM needs all outputs on one handle (replicate the model, shard the points)"); return GPMPC_ERR_STATE; }
     if (!Sigma) { set_error(h, "EM needs an input covariance"); return GPMPC_ERR_ARG; }
     const int npairs = Ny * (Ny + 1) / 2;
