@@ -93,7 +93,7 @@ struct gpmpc_handle_s {
     bool has_data = false, has_hyper = false, factorized = false;
     // EM scratch
     double *dEmTr = nullptr, *dEMP = nullptr, *dEmE = nullptr, *dEmF = nullptr, *dEmW = nullptr, *dEmIJ = nullptr;
-    double *dEmMeanPart = nullptr, *dEmPart = nullptr, *dEmLQ = nullptr;
+    double *dEmMeanPart = nullptr, *dEmPart = nullptr, *dEmLQ = nullptr, *dEmVec = nullptr;
     int emHcap = 0;
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
@@ -278,14 +278,18 @@ static int launch_kbuild(gpmpc_handle_t h, const double* dHyp, const double* dJi
     const int KD = (h->Nx + 3) & ~3, S = ((KD >> 2) & 1) ? KD : KD + 4;
     const int smem = (2 * KB2_TILE * S + 2 * KB2_TILE + 256) * 8;
     if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
-        CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (2 * KB2_TILE * 36 + 2 * KB2_TILE + 256) * 8));
+        CUDA_TRY(cudaFuncSetAttribute(kbuild_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * KB2_TILE * 36 + 2 * KB2_TILE + 256) * 8));
         conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
     }
     const int T = h->Npad / KB2_TILE;
     dim3 grid(T * (T + 1) / 2, 1, batch);
-    kbuild_dmma_kernel<<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dMu, dHyp, h->Nx + 2, dJit,
-                                                    K, h->Npad, slab(h), full);
+    if (full)
+        kbuild_dmma_kernel<true><<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dMu, dHyp, h->Nx + 2, dJit, K, h->Npad, slab(h));
+    else
+        kbuild_dmma_kernel<false><<<grid, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dMu, dHyp, h->Nx + 2, dJit, K, h->Npad, slab(h));
     CUDA_TRY(cudaGetLastError());
     return GPMPC_OK;
 }
@@ -455,7 +459,7 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     if (h->hPeerStatus) cudaFreeHost(h->hPeerStatus);
     double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
                       h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dR2, h->dCovV, h->dCovOut, h->dUall, h->dBeta, h->dPDV, h->dPH, h->dGradOut, h->dG, h->dIn, h->dOut, h->dU, h->dKinv, h->dGradPart, h->dGrad,
-                      h->dEmTr, h->dEmLQ, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
+                      h->dEmTr, h->dEmLQ, h->dEmVec, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
     if (h->hPinned) cudaFreeHost(h->hPinned);
@@ -742,6 +746,8 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
 // ------------------------------------------------------------------------------------
 // predict
 // ------------------------------------------------------------------------------------
+static inline int ks_chunk(gpmpc_handle_t h);
+
 static int ensure_predict_bufs(gpmpc_handle_t h, int H)
 {
     const long long np = h->Npad;
@@ -752,7 +758,7 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
         h->psk_ctas = 2 * sms;
         const long long nt = np / 128;
         ALLOC(h->dKST, (long long)h->nloc * HB * np);
-        ALLOC(h->dPMJ, (long long)h->nloc * HB * ((np + 1023) / 1024) * (h->Nx + 1));
+        ALLOC(h->dPMJ, (long long)h->nloc * HB * ((np + ks_chunk(h) - 1) / ks_chunk(h)) * (h->Nx + 1));
         ALLOC(h->dSQ, (long long)h->nloc * HB * nt);
         ALLOC(h->dCnt, (long long)h->nloc * nt + h->nloc + 1);
     }
@@ -807,8 +813,15 @@ static cudaError_t psk_launch_bm(const PredictParams& p, const double* A, long l
     CUtensorMap tmA, tmB;
     if (!tmap_make(&tmA, A, np, BM, np, sA, p.nloc, BM)) return cudaErrorInvalidValue;
     if (!tmap_make(&tmB, B, np, np, np, sB, p.nloc, PSK_BN)) return cudaErrorInvalidValue;
-    kern<<<grid, PSK_THREADS, BYTES, st>>>(p, tmA, tmB);
-    return cudaGetLastError();
+    // programmatic dependent launch after the ks kernel (the kernel's griddepcontrol.wait guards its inputs)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PSK_THREADS); cfg.dynamicSmemBytes = BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p, tmA, tmB);
 }
 
 static cudaError_t psk_launch(int bm, const PredictParams& p, const double* A, long long sA, const double* B, long long sB,
@@ -848,30 +861,36 @@ static void psk_base(gpmpc_handle_t h, PredictParams& p, int Hc)
     p.hyp = h->dHyp; p.hyp_ld = h->Nx + 2; p.Nx = h->Nx;
 }
 
-static inline int ks_chunk(gpmpc_handle_t h) { return h->Npad <= 4096 ? 1024 : KS_CHUNK; }
+// training points per CTA of the ks kernel: the chunk of X^T lives in shared memory (Nx * chunk doubles)
+static inline int ks_chunk(gpmpc_handle_t h) { return h->Nx <= 12 ? 1024 : (h->Nx <= 24 ? 512 : 256); }
 
-template <int NXP>
+template <int NXP, int CH>
 static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
-    dim3 g(nblk, bm, h->nloc);
-    if (ks_chunk(h) == 1024)
-        ks_mean_jac_kernel<NXP, 1024><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
-                                                             dZc, Hc, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
-    else
-        ks_mean_jac_kernel<NXP, KS_CHUNK><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
-                                                                 dZc, Hc, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
+    constexpr int HG = 8;
+    auto kern = ks_rows_kernel<NXP, CH, HG>;
+    const int smem = h->Nx * CH * 8;
+    static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
+    if (smem > 48 * 1024 && !conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NXP * CH * 8);
+        if (e != cudaSuccess) return e;
+        conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
+    }
+    dim3 g(nblk, (bm + HG - 1) / HG, h->nloc);
+    kern<<<g, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
+                                  dZc, Hc, bm, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
     return cudaGetLastError();
 }
 
 static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
     const int Nx = h->Nx;       // register-array extent NXP: next multiple of 4 up to 16, then 24 / 32
-    if (Nx <= 4) return launch_ks<4>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 8) return launch_ks<8>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 12) return launch_ks<12>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 16) return launch_ks<16>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 24) return launch_ks<24>(h, dZc, Hc, bm, nblk);
-    return launch_ks<32>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 4) return launch_ks<4, 1024>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 8) return launch_ks<8, 1024>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 12) return launch_ks<12, 1024>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 16) return launch_ks<16, 512>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 24) return launch_ks<24, 512>(h, dZc, Hc, bm, nblk);
+    return launch_ks<32, 256>(h, dZc, Hc, bm, nblk);
 }
 
 // rows of Amat (h-major, stride HB*np per output) times T^T with T = Li or L (lower triangular):
@@ -927,8 +946,8 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
     as.flags = use_peers ? reinterpret_cast<const unsigned long long*>(h->dPeerBlock) + (h->peer_step & 1) * GPMPC_MAXW : nullptr;
     as.world = h->world; as.step = h->peer_step; as.status = h->dPeerStatus; as.timeout_clocks = timeout_clocks;
     // one chunk and no NCCL call in between: the product kernel's last CTA assembles too (2 launches per step)
-    // (its 8 warps each need 2 Ny Nx + Ny doubles of the pipeline's shared memory: >= 68 KB at the smallest tile)
-    const bool fused_assemble = (H <= HB) && !nccl_gather && (8 * (2 * h->Ny * Nx + h->Ny) * 8 <= 64 * 1024);
+    // (it keeps J Sigma for all H points in the pipeline's shared memory: H Ny Nx doubles, >= 68 KB available)
+    const bool fused_assemble = (H <= HB) && !nccl_gather && ((long long)H * h->Ny * Nx * 8 <= 64 * 1024);
     for (int h0 = 0; h0 < H; h0 += HB) {
         const int Hc = std::min(HB, H - h0);
         const int bm = (Hc + 7) / 8 * 8;
@@ -1072,6 +1091,7 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
     if (!h->dEmTr) {
         ALLOC(h->dEmTr, (long long)Ny * ntr);
         ALLOC(h->dEmLQ, (long long)Ny * np);
+        ALLOC(h->dEmVec, 2LL * np + Ny);
         ALLOC(h->dEmE, (long long)npairs * np); ALLOC(h->dEmF, (long long)npairs * np);
         ALLOC(h->dEmW, (long long)npairs * Nx * np); ALLOC(h->dEmIJ, (long long)npairs * Nx * np);
         ALLOC(h->dEmMeanPart, (long long)Ny * nblk); ALLOC(h->dEmPart, (long long)npairs * T * T);
@@ -1106,6 +1126,13 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
             em_pair_kernel<<<dim3(Tq, Tq, 1), 256, 2 * Nx * 64 * 8, h->st>>>(h->N, Nx, Ny, dP, h->dAlpha, np,
                                                                           h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmLQ, nullptr, 1, paa, h->dKinv, np);
             CUDA_TRY(cudaGetLastError());
+            // rank-one backbone: |L^-1 e^E|^2 (same kernels as alpha's first half)
+            em_qvec_kernel<<<(np + 255) / 256, 256, 0, h->st>>>(h->dEmE + (long long)paa * np, h->N, np, h->dEmVec);
+            CUDA_TRY(cudaGetLastError());
+            trmv_lower_kernel<<<dim3((np + 7) / 8, 1, 1), 256, 0, h->st>>>(h->dLi + (long long)a * slab(h), np, 0, h->dEmVec, 0, h->dEmVec + np, 0, np);
+            CUDA_TRY(cudaGetLastError());
+            sumsq_kernel<<<1, 256, 0, h->st>>>(h->dEmVec + np, np, h->dEmVec + 2LL * np + a);
+            CUDA_TRY(cudaGetLastError());
             GemmParams gp;
             memset(&gp, 0, sizeof(gp));
             gp.A = h->dLi + (long long)a * slab(h); gp.lda = np;
@@ -1118,7 +1145,7 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
             CUDA_TRY(cudaGetLastError());
         }
         em_finalize_kernel<<<1, 1024, 0, h->st>>>(Nx, Ny, npairs, dP, h->dHyp, Nx + 2, h->dEmMeanPart, nblk, h->dEmPart, T * T,
-                                                   h->dEmTr, ntr,
+                                                   h->dEmTr, ntr, h->dEmVec + 2LL * np,
                                                    h->dMean + (size_t)p * Ny, h->dVar + (size_t)p * Ny, h->dCov + (size_t)p * Ny * Ny);
         CUDA_TRY(cudaGetLastError());
     }

@@ -106,14 +106,42 @@ __device__ __forceinline__ double exp2_t256(double t, const double* __restrict__
     p = fma(p, f, 0.6931471805599453);
     p = fma(p, f, 1.0);
     p *= T256[n & 255];
-    return __hiloint2double(__double2hiint(p) + ((n >> 8) << 20), __double2loint(p));
+    const int e = max(n >> 8, -1021);                // underflow: clamp the exponent (values below 2^-1021 are not needed)
+    return __hiloint2double(__double2hiint(p) + (e << 20), __double2loint(p));
+}
+
+// same with the 16-entry table (c_exp2_tab, one entry per shared-memory bank => conflict-free) and a
+// degree-7 polynomial on |f| <= 1/32
+__constant__ double c_exp2_tab[16] = {
+    1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721,
+    1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951,
+    1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429,
+    1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+__device__ __forceinline__ double exp2_t16(double t, const double* __restrict__ T16)
+{
+    const double SH = 6755399441055744.0;
+    const double s = fma(t, 16.0, SH);
+    const int n = __double2loint(s);
+    const double f = fma(s - SH, -0.0625, t);        // |f| <= 1/32, exact
+    double p = 1.5252733804059838e-05;               // (ln 2)^k / k!, k = 7..1
+    p = fma(p, f, 0.00015403530393381606);
+    p = fma(p, f, 0.0013333558146428441);
+    p = fma(p, f, 0.009618129107628477);
+    p = fma(p, f, 0.055504108664821576);
+    p = fma(p, f, 0.2402265069591007);
+    p = fma(p, f, 0.6931471805599453);
+    p = fma(p, f, 1.0);
+    p *= T16[n & 15];
+    const int e = max(n >> 4, -1021);
+    return __hiloint2double(__double2hiint(p) + (e << 20), __double2loint(p));
 }
 
 #define KB2_TILE 128
+template <bool FULL>
 __global__ void __launch_bounds__(256)
 kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const double* __restrict__ mu,
                    const double* __restrict__ hyp, int hyp_ld, const double* __restrict__ jitter,
-                   double* __restrict__ K, int ld, long long sK, int full)
+                   double* __restrict__ K, int ld, long long sK)
 {
     extern __shared__ double sm[];
     const int KD = (Nx + 3) & ~3;                         // k extent of the MMA, zero padded
@@ -141,7 +169,10 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
         sc[tid] = (tid < Nx) ? 1.2011224087864498 / hp[tid] : 0.0;
         mus[tid] = (tid < Nx) ? mu[tid] : 0.0;
     }
-    T256[tid] = c_exp2_tab256[tid];
+    // the full build is store-bound: it takes the 16-entry table (one entry per shared-memory bank: conflict-free);
+    // the lower-only build is instruction-bound: 256 entries buy a degree-4 instead of a degree-7 polynomial
+    if (FULL) { if (tid < 16) T256[tid] = c_exp2_tab[tid]; }
+    else T256[tid] = c_exp2_tab256[tid];
     __syncthreads();
     {   // scaled, centred coordinates of the 128 row points (tid < 128) / column points
         const int p = (tid < KB2_TILE) ? i0 + tid : j0 + tid - KB2_TILE;
@@ -161,7 +192,7 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
     const double dg = hp[Nx + 1] * hp[Nx + 1] + (jitter ? jitter[a] : 0.0);
     double* Ka = K + (long long)a * sK;
     const bool offdiag = (bi != bj);
-    const bool mirror = full && offdiag;
+    const bool mirror = FULL && offdiag;
     // tiles that touch the diagonal or the identity tail take the checked epilogue
     const bool special = !offdiag || (i0 + KB2_TILE > N) || (j0 + KB2_TILE > N);
     const int nk4 = KD >> 2;
@@ -188,8 +219,12 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
             for (int q = 0; q < 4; ++q) {
                 const int cl0 = ng * 32 + q * 8;          // + 2t folded into the base pointers
                 const double2 qc = *reinterpret_cast<const double2*>(qj + cl0 + 2 * t);
-                double v0 = exp2_t256(fmax(fmin((qr + qc.x) + acc[q][0], l2sf2), -1020.0), T256);
-                double v1 = exp2_t256(fmax(fmin((qr + qc.y) + acc[q][1], l2sf2), -1020.0), T256);
+                // log2 k: the lower clamp lives inside exp2 (integer max on the exponent); the upper clamp (k <= sf2
+                // despite rounding) only matters where the distance is 0, i.e. on diagonal tiles
+                double t0 = (qr + qc.x) + acc[q][0], t1 = (qr + qc.y) + acc[q][1];
+                if (special) { t0 = fmin(t0, l2sf2); t1 = fmin(t1, l2sf2); }
+                double v0 = FULL ? exp2_t16(t0, T256) : exp2_t256(t0, T256);
+                double v1 = FULL ? exp2_t16(t1, T256) : exp2_t256(t1, T256);
                 if (special) {
                     const int col = j0 + cl0 + 2 * t;
                     if (row == col) v0 += dg;
@@ -328,6 +363,7 @@ __device__ __forceinline__ void warp_potrf16_trtri16(double* D, double* Dinv, in
             a[k] = fma(-a[j], lkj, a[k]);                  // meaningful for r >= k; upper part is never read
         }
     }
+    __syncwarp();
     if (lane < 16) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) if (k <= r) D[r * LF_LD + k] = a[k];
@@ -541,6 +577,7 @@ __device__ __forceinline__ void warp_potrf16(double* D, double* ipd, int* info, 
             a[k] = fma(-a[j], lkj, a[k]);                  // meaningful for r >= k; upper part is never read
         }
     }
+    __syncwarp();                                           // lanes 16..31 read the same rows above (ordered by the shuffles; explicit for racecheck)
     if (lane < 16) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) if (k <= r) D[r * LF_LD + k] = a[k];
@@ -908,80 +945,100 @@ logdet_dot_kernel(const double* __restrict__ L, int ld, long long sL,
 //   ks_i = covSE(X_i, z)               gp_functions.py:114-117,132
 //   mean = ks^T alpha                  gp_functions.py:119-120,135
 //   J_d  = sum_i alpha_i ks_i (X_id - z_d)/ell_d^2   (closed form of ca.jacobian, :146-147)
-//   KST[a][h][i] (h-major) is the B^T operand of the v = Linv ks tensor-core product.
-//   grid (Npad/1024, BM rows, outputs); rows h >= H are zero-filled.
+//   KST[a][h][i] (h-major) is the A operand of the v = Linv ks tensor-core product; rows h >= H are zero-filled.
+// One CTA keeps its chunk of training inputs in shared memory and loops over HG test points, so X^T is
+// read from L2 once per HG rows instead of once per row (the r1 kernel, one CTA per row, moved 587 MB
+// through L2 per C5 step and ran at L2 bandwidth: 85 us for ~25 us of arithmetic).
+// grid (Npad/CH, ceil(BM/HG), outputs).
 // ---------------------------------------------------------------------------------------
-#define KS_CHUNK 2048          // points per CTA for large N (1024 when Npad <= 4096: more CTAs)
-template <int NXP, int CH>
+template <int NXP, int CH, int HG>
 __global__ void __launch_bounds__(256)
-ks_mean_jac_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
-                   const double* __restrict__ hyp, int hyp_ld,
-                   const double* __restrict__ alpha, long long sal,
-                   const double* __restrict__ Z, int H,
-                   double* __restrict__ KST, int ldk, long long sK,
-                   double* __restrict__ PMJ, int nblk)
+ks_rows_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
+               const double* __restrict__ hyp, int hyp_ld,
+               const double* __restrict__ alpha, long long sal,
+               const double* __restrict__ Z, int H, int BMrows,
+               double* __restrict__ KST, int ldk, long long sK,
+               double* __restrict__ PMJ, int nblk)
 {
+    extern __shared__ double Xs[];                         // [Nx][CH]
     __shared__ double red[8][NXP + 1];
-    __shared__ double zs[NXP], ie[NXP], ie2[NXP];
-    const int a = blockIdx.z, h = blockIdx.y, blk = blockIdx.x;
-    const int tid = threadIdx.x;
-    double* krow = KST + (long long)a * sK + (long long)h * ldk;
-    if (h >= H) {
-        for (int q = 0; q < CH / 256; ++q) {
-            const int i = blk * CH + tid + 256 * q;
-            if (i < ldk) krow[i] = 0.0;
-        }
-        return;
-    }
+    __shared__ double zs[HG][NXP], ie[NXP], ie2[NXP];
+    // let the dependent product kernel start launching once every CTA of this grid is resident (it waits
+    // for this grid's completion before reading KS^T): hides its launch latency and prologue
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int a = blockIdx.z, hg = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+    const int i0 = blk * CH;
     const double* hp = hyp + (long long)a * hyp_ld;
+    for (int idx = tid; idx < Nx * CH; idx += 256) {
+        const int d = idx / CH, r = idx - d * CH;
+        Xs[idx] = (i0 + r < ldx) ? XT[(long long)d * ldx + i0 + r] : 0.0;
+    }
     if (tid < NXP) {
         const double e = (tid < Nx) ? hp[tid] : 1.0;
-        zs[tid] = (tid < Nx) ? Z[(long long)h * Nx + tid] : 0.0;
         ie[tid] = 1.0 / e;
         ie2[tid] = 1.0 / (e * e);
     }
+    for (int idx = tid; idx < HG * NXP; idx += 256) {
+        const int r = idx / NXP, d = idx - r * NXP, h = hg * HG + r;
+        zs[r][d] = (d < Nx && h < H) ? Z[(long long)h * Nx + d] : 0.0;
+    }
     __syncthreads();
     const double sf2 = hp[Nx] * hp[Nx];
-    double am = 0.0, aj[NXP];
-#pragma unroll
-    for (int d = 0; d < NXP; ++d) aj[d] = 0.0;
     const double* al = alpha + (long long)a * sal;
-    for (int q = 0; q < CH / 256; ++q) {
-        const int i = blk * CH + tid + 256 * q;
-        double ks = 0.0;
-        if (i < N) {
-            double dist = 0.0, df[NXP];
+    double alv[CH / 256];
 #pragma unroll
-            for (int d = 0; d < NXP; ++d) {
-                df[d] = 0.0;
-                if (d < Nx) {
-                    df[d] = XT[(long long)d * ldx + i] - zs[d];
-                    const double s = df[d] * ie[d];
-                    dist = fma(s, s, dist);
-                }
-            }
-            ks = sf2 * exp(-0.5 * dist);
-            const double w = al[i] * ks;
-            am += w;
+    for (int q = 0; q < CH / 256; ++q) { const int i = i0 + tid + 256 * q; alv[q] = (i < N) ? al[i] : 0.0; }
+    for (int r = 0; r < HG; ++r) {
+        const int h = hg * HG + r;
+        if (h >= BMrows) break;
+        double* krow = KST + (long long)a * sK + (long long)h * ldk;
+        if (h >= H) {                                      // padding rows of the A operand: zeros
 #pragma unroll
-            for (int d = 0; d < NXP; ++d) aj[d] = fma(w, df[d], aj[d]);
+            for (int q = 0; q < CH / 256; ++q) { const int i = i0 + tid + 256 * q; if (i < ldk) krow[i] = 0.0; }
+            continue;
         }
-        if (i < ldk) krow[i] = ks;
-    }
-    am = warp_sum(am);
+        double am = 0.0, aj[NXP];
 #pragma unroll
-    for (int d = 0; d < NXP; ++d) aj[d] = warp_sum(aj[d]);
-    if ((tid & 31) == 0) {
-        red[tid >> 5][0] = am;
+        for (int d = 0; d < NXP; ++d) aj[d] = 0.0;
 #pragma unroll
-        for (int d = 0; d < NXP; ++d) red[tid >> 5][d + 1] = aj[d];
-    }
-    __syncthreads();
-    if (tid <= Nx) {
-        double s = 0.0;
-        for (int q = 0; q < 8; ++q) s += red[q][tid];
-        if (tid > 0) s *= ie2[tid - 1];
-        PMJ[(((long long)a * H + h) * nblk + blk) * (Nx + 1) + tid] = s;
+        for (int q = 0; q < CH / 256; ++q) {
+            const int il = tid + 256 * q, i = i0 + il;
+            double ks = 0.0;
+            if (i < N) {
+                double dist = 0.0, df[NXP];
+#pragma unroll
+                for (int d = 0; d < NXP; ++d) {
+                    df[d] = 0.0;
+                    if (d < Nx) {
+                        df[d] = Xs[d * CH + il] - zs[r][d];
+                        const double sc = df[d] * ie[d];
+                        dist = fma(sc, sc, dist);
+                    }
+                }
+                ks = sf2 * exp(-0.5 * dist);
+                const double w = alv[q] * ks;
+                am += w;
+#pragma unroll
+                for (int d = 0; d < NXP; ++d) aj[d] = fma(w, df[d], aj[d]);
+            }
+            if (i < ldk) krow[i] = ks;
+        }
+        am = warp_sum(am);
+#pragma unroll
+        for (int d = 0; d < NXP; ++d) aj[d] = warp_sum(aj[d]);
+        __syncthreads();                                   // red[] of the previous row has been consumed
+        if ((tid & 31) == 0) {
+            red[tid >> 5][0] = am;
+#pragma unroll
+            for (int d = 0; d < NXP; ++d) red[tid >> 5][d + 1] = aj[d];
+        }
+        __syncthreads();
+        if (tid <= Nx) {
+            double sacc = 0.0;
+            for (int q = 0; q < 8; ++q) sacc += red[q][tid];
+            if (tid > 0) sacc *= ie2[tid - 1];
+            PMJ[(((long long)a * H + h) * nblk + blk) * (Nx + 1) + tid] = sacc;
+        }
     }
 }
 
@@ -1267,7 +1324,10 @@ em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
         for (int c = 0; c < 4; ++c) {
             const int j = j0 + tx + 16 * c;
             const double lq = (i < N && j < N) ? E[(long long)p * ldn + i] + F[(long long)p * ldn + j] + 2.0 * acc[r][c] : 0.0;
-            if (mode) { if (i < ldq && j < ldq) Qout[(long long)i * ldq + j] = (i < N && j < N) ? exp(lq) : 0.0; }
+            // mode 1 stores only the part of Q beyond its rank-one backbone: Q_ij = e^{E_i} e^{F_j} (1 + expm1(2 acc_ij));
+            // the backbone's trace term |L^-1 e^E|^2 is formed like the ME variance (em_qvec_kernel + trmv), which keeps
+            // EM -> ME exact to ~1e-11 as Sigma -> 0 instead of amplifying the full Q through L^-1 twice
+            if (mode) { if (i < ldq && j < ldq) Qout[(long long)i * ldq + j] = (i < N && j < N) ? exp(E[(long long)p * ldn + i] + F[(long long)p * ldn + j]) * expm1(2.0 * acc[r][c]) : 0.0; }
             else if (i < N && j < N) {
                 // beta_i beta_j (t Q_ij - q_i q_j) = (beta_i q_i)(beta_j q_j) expm1(log t + log Q_ij - log q_i - log q_j):
                 // the reference's  t beta^T Q beta - mean_a mean_b  (:412,416) term by term, before the sums cancel
@@ -1285,6 +1345,30 @@ em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
         double r = 0.0;
         for (int w = 0; w < 8; ++w) r += red[w];
         part[((long long)p * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = r;
+    }
+}
+
+// rank-one backbone of Q_aa: qv_i = exp(E_i) (i < N, else 0)
+__global__ void em_qvec_kernel(const double* __restrict__ E, int N, int n, double* __restrict__ qv)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) qv[i] = (i < N) ? exp(E[i]) : 0.0;
+}
+
+// out[0] = sum_i v_i^2 (single block, fixed order)
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const double* __restrict__ v, int n, double* __restrict__ out)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s = fma(v[i], v[i], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int w = 0; w < 8; ++w) r += red[w];
+        out[0] = r;
     }
 }
 
@@ -1320,7 +1404,7 @@ __global__ void em_finalize_kernel(int Nx, int Ny, int npairs, const double* __r
                                    const double* __restrict__ hyp, int hyp_ld,
                                    const double* __restrict__ meanPart, int nblk,
                                    const double* __restrict__ part, int ntile2,
-                                   const double* __restrict__ trPart, int ntr,
+                                   const double* __restrict__ trPart, int ntr, const double* __restrict__ trVec,
                                    double* __restrict__ mean, double* __restrict__ var, double* __restrict__ cov)
 {
     __shared__ double mu[64];
@@ -1340,7 +1424,7 @@ __global__ void em_finalize_kernel(int Nx, int Ny, int npairs, const double* __r
         double c = s;       // = t beta_a^T Q beta_b - mean_a mean_b, summed term by term without the cancellation
         if (a == b) {
             // + expected variance  sf2 - t tr(K^-1 Q_aa)  from the Cholesky-based trace (two positive numbers)
-            double tr = 0.0;
+            double tr = trVec[a];                                 // |L^-1 e^E|^2: the rank-one backbone
             for (int q = 0; q < ntr; ++q) tr += trPart[(long long)a * ntr + q];
             const double sf = hyp[(long long)a * hyp_ld + Nx];
             c += sf * sf - P[nn] * tr;

@@ -115,6 +115,47 @@ __device__ __forceinline__ void assemble_point(const AssembleArgs& A, int h, dou
     if (WARP) __syncwarp(); else __syncthreads();
 }
 
+// all H points at once by one CTA (the fused tail of the product kernel): flat index spaces instead of a
+// point at a time, so the 256 threads stay busy -- phase A: outputs mean/var/J and JS = J Sigma into shared
+// memory (H Ny Nx doubles), phase B: cov.  Same arithmetic and summation order as assemble_point.
+__device__ __forceinline__ void assemble_flat(const AssembleArgs& A, double* JS, int tid, int nth)
+{
+    const int Ny = A.Ny, Nx = A.Nx, H = A.H, NyNx = Ny * Nx;
+    const bool ta = A.cov && A.method_ta;
+    for (int idx = tid; idx < H * NyNx; idx += nth) {
+        const int h = idx / NyNx, r = idx - h * NyNx, a = r / Nx, e = r - a * Nx;
+        const double* g = A.G + (((long long)a) * H + h) * (Nx + 2) + 2;
+        if (A.J) A.J[idx] = __ldcg(g + e);                      // (h, a, e) is the output's own layout
+        if (ta) {
+            const double* Sg = A.Sigma + (A.sigma_per_point ? (long long)h * Nx * Nx : 0);
+            double s = 0.0;
+            for (int d = 0; d < Nx; ++d) s = fma(__ldcg(g + d), Sg[d * Nx + e], s);
+            JS[idx] = s;
+        }
+    }
+    for (int idx = tid; idx < H * Ny; idx += nth) {
+        const int h = idx / Ny, a = idx - h * Ny;
+        const double* g = A.G + (((long long)a) * H + h) * (Nx + 2);
+        if (A.mean) A.mean[idx] = __ldcg(g);
+        if (A.var) A.var[idx] = __ldcg(g + 1);
+    }
+    __syncthreads();
+    if (A.cov) {
+        for (int idx = tid; idx < H * Ny * Ny; idx += nth) {
+            const int h = idx / (Ny * Ny), r = idx - h * Ny * Ny, a = r / Ny, b = r - a * Ny;
+            double s = (a == b) ? __ldcg(A.G + (((long long)a) * H + h) * (Nx + 2) + 1) : 0.0;
+            if (ta) {
+                const double* gb = A.G + (((long long)b) * H + h) * (Nx + 2) + 2;
+                const double* js = JS + (h * Ny + a) * Nx;
+                double t = 0.0;
+                for (int e = 0; e < Nx; ++e) t = fma(js[e], __ldcg(gb + e), t);
+                s += t;
+            }
+            A.cov[idx] = s;
+        }
+    }
+}
+
 // peer mode: acquire every source rank's flag for this step; false = a rank never showed up
 __device__ __forceinline__ bool peer_acquire(const AssembleArgs& A, int tid, int* sh_ok)
 {
@@ -221,11 +262,7 @@ __device__ __forceinline__ void psk_step_tail(const PredictParams& p, double* sh
     }
     if (p.do_assemble) {
         __threadfence();
-        // one warp per test point (a single CTA is assembling: 8 points in flight instead of 1)
-        if (peer_acquire(p.as, tid, s_ok)) {
-            double* shw = sh + (tid >> 5) * (2 * p.as.Ny * p.as.Nx + p.as.Ny);
-            for (int h = tid >> 5; h < p.as.H; h += nth >> 5) assemble_point<true>(p.as, h, shw, tid & 31, 32);
-        }
+        if (peer_acquire(p.as, tid, s_ok)) assemble_flat(p.as, sh, tid, nth);
     }
 }
 
@@ -313,6 +350,10 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
         s_pg = pg + 1;
     };
     constexpr int AHEAD = 2;           // prefetch distance in steps
+    // programmatic dependent launch: everything above overlapped the tail of the ks kernel; its output
+    // (KS^T, the partial mean / Jacobian sums) is only touched below this point.  A no-op when the
+    // kernel was launched without the attribute.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
         PskIter it;
         psk_iter_init(it, g0, p.T);

@@ -339,6 +339,39 @@ class GP:
             mean = self.inverse_mean(mean, self.__meanY, self.__stdY)
         return mean, c
 
+    def predict_batch_grad(self, x, u, cov=None, method=None):
+        """predict_batch plus the first derivatives CasADi's AD extracts from the symbolic GP when nlpsol
+        differentiates the MPC's NLP (mpc_class.py:390-412, :496-513): a dict with
+            mean (H,Ny)           de-standardised, as predict_batch
+            cov  (H,Ny,Ny)        standardised units (q4)
+            dmean_dz (H,Ny,Nx)    d mean / d [x,u] in the CALLER's units (chain rule through the scalers)
+            dcov_dz  (H,Ny,Ny,Nx) d cov / d [x,u]  (cov itself is not rescaled, so only 1/stdZ enters)
+            dcov_dSigma_factor (H,Ny,Nx)  J with d cov[a][b] / d Sigma[d][e] = J[a][d] J[b][e] ('TA')
+        Methods 'ME' and 'TA'.  This is what a casadi.Callback's Jacobian function returns; the same
+        numbers are available to `casadi.external` through gp_b200 / jac_gp_b200 (include/gpmpc_casadi.h)."""
+        method = method or self.__gp_method
+        if method not in ('ME', 'TA'):
+            raise NotImplementedError("derivatives are available for gp_method 'ME' and 'TA'")
+        if self.__comm.world > 1 and self.__mode == 'outputs':
+            raise NotImplementedError('predict_batch_grad needs all outputs on one GPU (build the GP with a single-process Comm)')
+        x = np.asarray(x, dtype=np.float64).reshape(-1, self.__Ny)
+        u = np.asarray(u, dtype=np.float64).reshape(x.shape[0], self.__Nu)
+        if self.__normalize:
+            x = self.standardize(x, self.__meanX, self.__stdX)
+            u = self.standardize(u, self.__meanU, self.__stdU)
+        Z = np.hstack([x, u])
+        if cov is None and method == 'TA':
+            cov = np.zeros((self.__Nx, self.__Nx))
+        g = self.__engine.predict_grad(Z, cov if method == 'TA' else None, _GPU_METHODS[method])
+        mean, jac, dcov = g['mean'], g['jac'], g['dcov_dz']
+        out = dict(cov=g['cov'], dcov_dSigma_factor=jac.copy())
+        if self.__normalize:
+            mean = self.inverse_mean(mean, self.__meanY, self.__stdY)
+            jac = jac * self.__stdY[None, :, None] / self.__stdZ[None, None, :]
+            dcov = dcov / self.__stdZ[None, None, None, :]
+        out.update(mean=mean, dmean_dz=jac, dcov_dz=dcov)
+        return out
+
     def predict(self, x, u, cov):
         """ Predict future state  (reference gp_class.py:245-263)
 
@@ -350,8 +383,9 @@ class GP:
         """
         if _is_symbolic(x) or _is_symbolic(u) or _is_symbolic(cov):
             raise NotImplementedError(
-                'symbolic (CasADi MX/SX) predict: wrap GP.predict_batch in a casadi.Callback as '
-                'described in INTEGRATION.md (SURVEY 8f row 1); CasADi is not available in this build')
+                'symbolic (CasADi MX/SX) predict: bind the engine with casadi.external("gp_b200", libgpmpc.so) or wrap '
+                'GP.predict_batch / predict_batch_grad in a casadi.Callback as described in INTEGRATION.md section 3 '
+                '(SURVEY 8f row 1); CasADi is not installed in this build, so that last Python step is not exercised here')
         x = np.asarray(x, dtype=np.float64).reshape(-1)
         u = np.asarray(u, dtype=np.float64).reshape(-1)
         mean, c = self.predict_batch(x.reshape(1, -1), u.reshape(1, -1),

@@ -405,6 +405,24 @@ def test_casadi_external_entry_points():
     lib.gp_b200_unbind()
     assert not lib.gp_b200_sparsity_in(0)
     eng.close()
+    # the GP-class view: derivatives in the caller's units (chain rule through the scalers) vs central
+    # differences of GP.predict_batch itself
+    gp, m = _gp_from_fixture('tank')
+    d = load_golden('derived', 'tank')
+    xs = np.tile(d['x0'], (3, 1)) * (1 + 0.02 * np.arange(3)[:, None]); us = np.tile(d['u0'], (3, 1))
+    gg = gp.predict_batch_grad(xs, us, d['Sigma'])
+    mb, cb = gp.predict_batch(xs, us, d['Sigma'])
+    assert np.array_equal(gg['mean'], mb) and np.array_equal(gg['cov'], cb)
+    zs = np.hstack([xs, us])
+    for e in range(6):
+        h = 1e-4 * max(1.0, abs(zs[0, e]))
+        zp = zs.copy(); zp[:, e] += h
+        zm = zs.copy(); zm[:, e] -= h
+        mp_, cp_ = gp.predict_batch(zp[:, :4], zp[:, 4:], d['Sigma'])
+        mm_, cm_ = gp.predict_batch(zm[:, :4], zm[:, 4:], d['Sigma'])
+        assert relinf(gg['dmean_dz'][:, :, e], (mp_ - mm_) / (2 * h)) < 1e-5
+        assert relinf(gg['dcov_dz'][:, :, :, e], (cp_ - cm_) / (2 * h)) < 2e-5
+    gp.close()
 
 
 # ------------------------------------------------------------------ 'EM' exact moment matching (8f row 2)
