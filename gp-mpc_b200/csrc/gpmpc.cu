@@ -93,7 +93,7 @@ struct gpmpc_handle_s {
     bool has_data = false, has_hyper = false, factorized = false;
     // EM scratch
     double *dEmTr = nullptr, *dEMP = nullptr, *dEmE = nullptr, *dEmF = nullptr, *dEmW = nullptr, *dEmIJ = nullptr;
-    double *dEmMeanPart = nullptr, *dEmPart = nullptr, *dEmLQ = nullptr, *dEmVec = nullptr;
+    double *dEmMeanPart = nullptr, *dEmPart = nullptr, *dEmLQ = nullptr, *dEmVec = nullptr, *dEmE2 = nullptr, *dEmF2 = nullptr;
     int emHcap = 0;
     std::vector<double> hyper;        // (nloc, Nx+2)
     std::vector<double> logdet, yalpha;
@@ -459,7 +459,7 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     if (h->hPeerStatus) cudaFreeHost(h->hPeerStatus);
     double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
                       h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dR2, h->dCovV, h->dCovOut, h->dUall, h->dBeta, h->dPDV, h->dPH, h->dGradOut, h->dG, h->dIn, h->dOut, h->dU, h->dKinv, h->dGradPart, h->dGrad,
-                      h->dEmTr, h->dEmLQ, h->dEmVec, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
+                      h->dEmTr, h->dEmLQ, h->dEmVec, h->dEmE2, h->dEmF2, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
     if (h->hPinned) cudaFreeHost(h->hPinned);
@@ -861,17 +861,19 @@ static void psk_base(gpmpc_handle_t h, PredictParams& p, int Hc)
     p.hyp = h->dHyp; p.hyp_ld = h->Nx + 2; p.Nx = h->Nx;
 }
 
-// training points per CTA of the ks kernel: the chunk of X^T lives in shared memory (Nx * chunk doubles)
-static inline int ks_chunk(gpmpc_handle_t h) { return h->Nx <= 12 ? 1024 : (h->Nx <= 24 ? 512 : 256); }
+// training points per CTA of the ks kernel: the chunk of X^T lives in shared memory (Nx * chunk doubles).
+// Small problems (Npad <= 4096) take 256-point chunks and 2 rows per CTA: there the kernel is latency-bound
+// and needs CTAs, not L2 savings.
+static inline bool ks_small(gpmpc_handle_t h) { return h->Npad <= 4096; }
+static inline int ks_chunk(gpmpc_handle_t h) { return ks_small(h) ? 256 : (h->Nx <= 12 ? 1024 : (h->Nx <= 24 ? 512 : 256)); }
 
-template <int NXP, int CH>
+template <int NXP, int CH, int HG>
 static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
-    constexpr int HG = 8;
     auto kern = ks_rows_kernel<NXP, CH, HG>;
     const int smem = h->Nx * CH * 8;
     static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
-    if (smem > 48 * 1024 && !conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
+    if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {      // static + dynamic may pass 48 KB
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NXP * CH * 8);
         if (e != cudaSuccess) return e;
         conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
@@ -885,12 +887,20 @@ static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm
 static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
     const int Nx = h->Nx;       // register-array extent NXP: next multiple of 4 up to 16, then 24 / 32
-    if (Nx <= 4) return launch_ks<4, 1024>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 8) return launch_ks<8, 1024>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 12) return launch_ks<12, 1024>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 16) return launch_ks<16, 512>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 24) return launch_ks<24, 512>(h, dZc, Hc, bm, nblk);
-    return launch_ks<32, 256>(h, dZc, Hc, bm, nblk);
+    if (ks_small(h)) {
+        if (Nx <= 4) return launch_ks<4, 256, 2>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 8) return launch_ks<8, 256, 2>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 12) return launch_ks<12, 256, 2>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 16) return launch_ks<16, 256, 2>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 24) return launch_ks<24, 256, 2>(h, dZc, Hc, bm, nblk);
+        return launch_ks<32, 256, 2>(h, dZc, Hc, bm, nblk);
+    }
+    if (Nx <= 4) return launch_ks<4, 1024, 8>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 8) return launch_ks<8, 1024, 8>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 12) return launch_ks<12, 1024, 8>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 16) return launch_ks<16, 512, 8>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 24) return launch_ks<24, 512, 8>(h, dZc, Hc, bm, nblk);
+    return launch_ks<32, 256, 8>(h, dZc, Hc, bm, nblk);
 }
 
 // rows of Amat (h-major, stride HB*np per output) times T^T with T = Li or L (lower triangular):
@@ -1034,7 +1044,7 @@ static void lu_solve(int n, const double* LU, const int* piv, double* B, int m)
 static int em_prepare_point(gpmpc_handle_t h, const double* S, double* out)
 {
     const int Nx = h->Nx, Ny = h->Ny, nn = Nx * Nx, m = Nx + 2;
-    std::vector<double> R(nn), B(nn);
+    std::vector<double> R(nn), B(nn), lc(Ny);
     std::vector<int> piv(Nx);
     double det = 0.0;
     for (int a = 0; a < Ny; ++a) {
@@ -1044,11 +1054,23 @@ static int em_prepare_point(gpmpc_handle_t h, const double* S, double* out)
         for (int i = 0; i < nn; ++i) B[i] = 0.0;
         for (int i = 0; i < Nx; ++i) B[i * Nx + i] = 1.0;
         lu_solve(Nx, R.data(), piv.data(), B.data(), Nx);                 // iR = (Sigma + Lambda)^-1   (:383-385)
-        double* o = out + (size_t)a * (nn + 1);
+        double* o = out + (size_t)a * (2 * nn + 2);
         memcpy(o, B.data(), nn * 8);
         double pe = 1.0;
         for (int d = 0; d < Nx; ++d) pe *= hp[d];
         o[nn] = hp[Nx] * hp[Nx] / sqrt(det) * pe;                         // c (:386-387)
+        // G_a = Lambda^-1 Sigma (Sigma + Lambda)^-1  (= Lambda^-1 - (Sigma+Lambda)^-1, formed without the subtraction)
+        for (int i = 0; i < Nx; ++i)
+            for (int j = 0; j < Nx; ++j) {
+                double sacc = 0.0;
+                for (int k = 0; k < Nx; ++k) sacc += S[i * Nx + k] * B[k * Nx + j];
+                o[nn + 1 + i * Nx + j] = sacc / (hp[i] * hp[i]);
+            }
+        // lc_a = log sf2_a - log c_a = 1/2 log det(I + Sigma Lambda^-1): determinant of I + small, not a difference of logs
+        for (int i = 0; i < Nx; ++i) for (int j = 0; j < Nx; ++j) R[i * Nx + j] = S[i * Nx + j] / (hp[j] * hp[j]) + (i == j ? 1.0 : 0.0);
+        if (!lu_factor(Nx, R.data(), piv.data(), &det) || !(det > 0.0)) { set_error(h, "EM: det(I + Sigma Lambda^-1) <= 0"); return GPMPC_ERR_ARG; }
+        lc[a] = 0.5 * log(det);
+        o[2 * nn + 1] = lc[a];
     }
     int p = 0;
     for (int a = 0; a < Ny; ++a)
@@ -1061,9 +1083,10 @@ static int em_prepare_point(gpmpc_handle_t h, const double* S, double* out)
             if (!lu_factor(Nx, R.data(), piv.data(), &det) || !(det > 0.0)) { set_error(h, "EM: det(R_ab) <= 0"); return GPMPC_ERR_ARG; }
             for (int i = 0; i < nn; ++i) B[i] = 0.5 * S[i];
             lu_solve(Nx, R.data(), piv.data(), B.data(), Nx);             // solve(R, Sigma/2)  (:402)
-            double* o = out + (size_t)Ny * (nn + 1) + (size_t)p * (nn + 3);
+            double* o = out + (size_t)Ny * (2 * nn + 2) + (size_t)p * (nn + 4);
             memcpy(o, B.data(), nn * 8);
             o[nn] = 1.0 / sqrt(det); o[nn + 1] = a; o[nn + 2] = b;        // t (:398)
+            o[nn + 3] = -0.5 * log(det) + lc[a] + lc[b];                  // log t + (log sf2_a - log c_a) + (log sf2_b - log c_b)
         }
     return GPMPC_OK;
 }
@@ -1073,7 +1096,7 @@ static cudaError_t launch_em_prep(gpmpc_handle_t h, int npairs, const double* dz
 {
     dim3 g(nblk, h->Ny + npairs);
     em_prep_kernel<NXP><<<g, 256, 0, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->Ny, npairs, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
-                                              dz, dEMP, h->dEmMeanPart, nblk, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->Npad, h->dEmLQ);
+                                              dz, dEMP, h->dEmMeanPart, nblk, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->Npad, h->dEmLQ, h->dEmE2, h->dEmF2);
     return cudaGetLastError();
 }
 
@@ -1086,13 +1109,14 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
     if (!Sigma) { set_error(h, "EM needs an input covariance"); return GPMPC_ERR_ARG; }
     const int npairs = Ny * (Ny + 1) / 2;
     if (npairs > 1024) { set_error(h, "EM supports Ny <= 44"); return GPMPC_ERR_ARG; }
-    const size_t per = (size_t)Ny * (nn + 1) + (size_t)npairs * (nn + 3);
+    const size_t per = (size_t)Ny * (2 * nn + 2) + (size_t)npairs * (nn + 4);
     const int nblk = (np + 255) / 256, T = (h->N + 63) / 64, Tq = np / 64, ntr = Tq * (Tq + 1) / 2;
     if (!h->dEmTr) {
         ALLOC(h->dEmTr, (long long)Ny * ntr);
         ALLOC(h->dEmLQ, (long long)Ny * np);
         ALLOC(h->dEmVec, 2LL * np + Ny);
         ALLOC(h->dEmE, (long long)npairs * np); ALLOC(h->dEmF, (long long)npairs * np);
+        ALLOC(h->dEmE2, (long long)npairs * np); ALLOC(h->dEmF2, (long long)npairs * np);
         ALLOC(h->dEmW, (long long)npairs * Nx * np); ALLOC(h->dEmIJ, (long long)npairs * Nx * np);
         ALLOC(h->dEmMeanPart, (long long)Ny * nblk); ALLOC(h->dEmPart, (long long)npairs * T * T);
     }
@@ -1118,13 +1142,13 @@ static int predict_em(gpmpc_handle_t h, int H, const double* Z, const double* Si
                       : (Nx <= 16) ? launch_em_prep<16>(h, npairs, dz, dP, nblk) : launch_em_prep<32>(h, npairs, dz, dP, nblk);
         CUDA_TRY(e);
         em_pair_kernel<<<dim3(T, T, npairs), 256, 2 * Nx * 64 * 8, h->st>>>(h->N, Nx, Ny, dP, h->dAlpha, np,
-                                                                          h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmLQ, h->dEmPart, 0, 0, nullptr, 0);
+                                                                          h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmLQ, h->dEmE2, h->dEmF2, h->dEmPart, 0, 0, nullptr, 0);
         CUDA_TRY(cudaGetLastError());
         // E[var] term of the diagonal pairs, Cholesky-based: t tr(K^-1 Q_aa) = t tr(L^-1 Q_aa L^-T)
         for (int a = 0; a < Ny; ++a) {
             const int paa = a * (a + 1) / 2 + a;
             em_pair_kernel<<<dim3(Tq, Tq, 1), 256, 2 * Nx * 64 * 8, h->st>>>(h->N, Nx, Ny, dP, h->dAlpha, np,
-                                                                          h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmLQ, nullptr, 1, paa, h->dKinv, np);
+                                                                          h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, np, h->dEmLQ, h->dEmE2, h->dEmF2, nullptr, 1, paa, h->dKinv, np);
             CUDA_TRY(cudaGetLastError());
             // rank-one backbone: |L^-1 e^E|^2 (same kernels as alpha's first half)
             em_qvec_kernel<<<(np + 255) / 256, 256, 0, h->st>>>(h->dEmE + (long long)paa * np, h->N, np, h->dEmVec);
@@ -1252,7 +1276,7 @@ static cudaError_t launch_grad_reduce(gpmpc_handle_t h, const double* dZc, int H
     dim3 g(nblk, Hc, h->nloc);
     const int smem = (h->Nx * 257 + 256) * 8;
     static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
-    if (smem > 48 * 1024 && !conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
+    if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {      // static + dynamic may pass 48 KB
         cudaError_t e = cudaFuncSetAttribute(grad_reduce_kernel<NXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (NX_MAX * 257 + 256) * 8);
         if (e != cudaSuccess) return e;
         conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);

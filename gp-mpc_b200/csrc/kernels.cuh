@@ -90,7 +90,7 @@ __constant__ double c_exp2_tab256[256] = {
     1.9571441241754002, 1.9624504802089273, 1.9677712232331759, 1.9731063922552343,
     1.9784560263879509, 1.9838201648502194, 1.9891988469672663, 1.9945921121709402};
 
-// 2^t for -1020 <= t <= ~1000 (the caller clamps): 256-entry table + degree-4 polynomial on
+// 2^t for -1020 <= t <= ~1000 (the CALLER clamps: rint(256 t) must fit the low word and the exponent stay normal): 256-entry table + degree-4 polynomial on
 // |f| <= 1/512 (truncation 3.8e-17), ~1.7 ulp.  Per value: 2 (rint by magic constant) + 1 (f) +
 // 4 (Horner) + table load + multiply + exponent insert -- the r1 kernel (16-entry table, degree 7)
 // was bound by issue slots (67 % active), not by HBM.
@@ -106,8 +106,7 @@ __device__ __forceinline__ double exp2_t256(double t, const double* __restrict__
     p = fma(p, f, 0.6931471805599453);
     p = fma(p, f, 1.0);
     p *= T256[n & 255];
-    const int e = max(n >> 8, -1021);                // underflow: clamp the exponent (values below 2^-1021 are not needed)
-    return __hiloint2double(__double2hiint(p) + (e << 20), __double2loint(p));
+    return __hiloint2double(__double2hiint(p) + ((n >> 8) << 20), __double2loint(p));
 }
 
 // same with the 16-entry table (c_exp2_tab, one entry per shared-memory bank => conflict-free) and a
@@ -132,8 +131,7 @@ __device__ __forceinline__ double exp2_t16(double t, const double* __restrict__ 
     p = fma(p, f, 0.6931471805599453);
     p = fma(p, f, 1.0);
     p *= T16[n & 15];
-    const int e = max(n >> 4, -1021);
-    return __hiloint2double(__double2hiint(p) + (e << 20), __double2loint(p));
+    return __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));
 }
 
 #define KB2_TILE 128
@@ -219,9 +217,9 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
             for (int q = 0; q < 4; ++q) {
                 const int cl0 = ng * 32 + q * 8;          // + 2t folded into the base pointers
                 const double2 qc = *reinterpret_cast<const double2*>(qj + cl0 + 2 * t);
-                // log2 k: the lower clamp lives inside exp2 (integer max on the exponent); the upper clamp (k <= sf2
-                // despite rounding) only matters where the distance is 0, i.e. on diagonal tiles
-                double t0 = (qr + qc.x) + acc[q][0], t1 = (qr + qc.y) + acc[q][1];
+                // log2 k, clamped from below (far-apart points under tiny length scales: SLSQP probes them); the upper clamp
+                // (k <= sf2 despite rounding) only matters where the distance is 0, i.e. on diagonal tiles
+                double t0 = fmax((qr + qc.x) + acc[q][0], -1020.0), t1 = fmax((qr + qc.y) + acc[q][1], -1020.0);   // 2^-1020 ~ 0
                 if (special) { t0 = fmin(t0, l2sf2); t1 = fmin(t1, l2sf2); }
                 double v0 = FULL ? exp2_t16(t0, T256) : exp2_t256(t0, T256);
                 double v1 = FULL ? exp2_t16(t1, T256) : exp2_t256(t1, T256);
@@ -1187,7 +1185,7 @@ gram_cov_kernel(const double* __restrict__ V, int ldv, long long sV, int n,
 // per launch set.  Host prepares the Nx x Nx quantities (gpmpc.cu, em_prepare_point):
 //   per output a :  iR_a = (Sigma + Lambda_a)^-1 ,  c_a = sf2_a prod(ell_a) / sqrt(det(Sigma+Lambda_a))
 //   per pair a>=b:  Qm = (Sigma (iL_a+iL_b) + I)^-1 Sigma/2 ,  t_ab = det(...)^-1/2
-// EMP layout (doubles): [a: iR (Nx*Nx), c] * Ny, then [pair: Qm (Nx*Nx), t, a, b] * npairs
+// EMP layout (doubles): [a: iR (Nx*Nx), c, G_a (Nx*Nx), lc_a] * Ny, then [pair: Qm (Nx*Nx), t, a, b, const_ab] * npairs
 // ---------------------------------------------------------------------------------------
 template <int NXP>
 __global__ void __launch_bounds__(256)
@@ -1196,9 +1194,9 @@ em_prep_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, int Ny, in
                const double* __restrict__ z, const double* __restrict__ EMP,
                double* __restrict__ meanPart, int nblk,
                double* __restrict__ E, double* __restrict__ F, double* __restrict__ W, double* __restrict__ IJ, int ldn,
-               double* __restrict__ LQ)
+               double* __restrict__ LQ, double* __restrict__ E2, double* __restrict__ F2)
 {
-    __shared__ double M[NXP * NXP];
+    __shared__ double M[NXP * NXP], Ga[NXP * NXP], Gb[NXP * NXP];
     __shared__ double red[8];
     const int role = blockIdx.y, tid = threadIdx.x;
     const int i = blockIdx.x * 256 + tid;
@@ -1208,7 +1206,7 @@ em_prep_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, int Ny, in
     for (int d = 0; d < NXP; ++d) v[d] = (d < Nx && i < N) ? XT[(long long)d * ldx + i] - z[d] : 0.0;
     if (role < Ny) {                                        // mean of output a (:381-388)
         const int a = role;
-        const double* P = EMP + (long long)a * (nn + 1);
+        const double* P = EMP + (long long)a * (2 * nn + 2);
         for (int q = tid; q < nn; q += 256) M[q] = P[q];
         __syncthreads();
         double quad = 0.0;
@@ -1236,9 +1234,13 @@ em_prep_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, int Ny, in
         return;
     }
     const int p = role - Ny;
-    const double* P = EMP + (long long)Ny * (nn + 1) + (long long)p * (nn + 3);
+    const double* P = EMP + (long long)Ny * (2 * nn + 2) + (long long)p * (nn + 4);
     const int a = (int)P[nn + 1], b = (int)P[nn + 2];
-    for (int q = tid; q < nn; q += 256) M[q] = P[q];
+    for (int q = tid; q < nn; q += 256) {
+        M[q] = P[q];
+        Ga[q] = EMP[(long long)a * (2 * nn + 2) + nn + 1 + q];      // G_a = Lambda_a^-1 Sigma (Sigma + Lambda_a)^-1
+        Gb[q] = EMP[(long long)b * (2 * nn + 2) + nn + 1 + q];
+    }
     __syncthreads();
     if (i >= ldn) return;
     const double* ha = hyp + (long long)a * hyp_ld;
@@ -1254,20 +1256,40 @@ em_prep_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, int Ny, in
             ii[d] = v[d] / (ha[d] * ha[d]); ij[d] = v[d] / (hb[d] * hb[d]);
         }
     }
-    double ei = lka, fj = lkb;
+    // e2 / f2: the SMALL parts only, for the cancellation-free pair sums:
+    //   log(t Q_ij) - log q_i - log q_j = const_ab + e2_i + f2_j + 2 ii^T M ij,
+    //   e2_i = ii^T M ii - 1/2 v^T G_a v   (log k_a(x_i) - log q^a_i = const - 1/2 v^T G_a v by Woodbury)
+    double e2 = 0.0, f2 = 0.0;
 #pragma unroll
     for (int e = 0; e < NXP; ++e) {
+        if (e < Nx) {
+            double wi = 0.0, wj = 0.0, ga = 0.0, gb = 0.0;
+#pragma unroll
+            for (int d = 0; d < NXP; ++d)
+                if (d < Nx) {
+                    wi = fma(ii[d], M[d * Nx + e], wi); wj = fma(ij[d], M[d * Nx + e], wj);
+                    ga = fma(v[d], Ga[d * Nx + e], ga); gb = fma(v[d], Gb[d * Nx + e], gb);
+                }
+            e2 = fma(wi, ii[e], e2); f2 = fma(wj, ij[e], f2);
+            e2 = fma(-0.5 * ga, v[e], e2); f2 = fma(-0.5 * gb, v[e], f2);
+            W[((long long)p * Nx + e) * ldn + i] = wi;
+            IJ[((long long)p * Nx + e) * ldn + i] = ij[e];
+        }
+    }
+    // E / F (with the big log k terms) serve the Q matrix of the trace term only
+    double ei = lka, fj = lkb;
+#pragma unroll
+    for (int e = 0; e < NXP; ++e)
         if (e < Nx) {
             double wi = 0.0, wj = 0.0;
 #pragma unroll
             for (int d = 0; d < NXP; ++d) if (d < Nx) { wi = fma(ii[d], M[d * Nx + e], wi); wj = fma(ij[d], M[d * Nx + e], wj); }
             ei = fma(wi, ii[e], ei); fj = fma(wj, ij[e], fj);
-            W[((long long)p * Nx + e) * ldn + i] = wi;
-            IJ[((long long)p * Nx + e) * ldn + i] = ij[e];
         }
-    }
     E[(long long)p * ldn + i] = ei;
     F[(long long)p * ldn + i] = fj;
+    E2[(long long)p * ldn + i] = (i < N) ? e2 : 0.0;
+    F2[(long long)p * ldn + i] = (i < N) ? f2 : 0.0;
 }
 
 // sum_ij beta_a,i beta_b,j (t Q_ij - q_i q_j) for one pair; 64x64 tile per CTA, 4x4 per thread (:394-416).
@@ -1282,16 +1304,17 @@ __global__ void __launch_bounds__(256)
 em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
                const double* __restrict__ alpha, long long sal,
                const double* __restrict__ E, const double* __restrict__ F, const double* __restrict__ W,
-               const double* __restrict__ IJ, int ldn, const double* __restrict__ LQ, double* __restrict__ part,
+               const double* __restrict__ IJ, int ldn, const double* __restrict__ LQ,
+               const double* __restrict__ E2, const double* __restrict__ F2, double* __restrict__ part,
                int mode, int pair_q, double* __restrict__ Qout, int ldq)
 {
     extern __shared__ double sm[];
     double* Ws = sm; double* Js = sm + Nx * 64;
     __shared__ double red[8];
     const int p = mode ? pair_q : blockIdx.z, nn = Nx * Nx;
-    const double* P = EMP + (long long)Ny * (nn + 1) + (long long)p * (nn + 3);
+    const double* P = EMP + (long long)Ny * (2 * nn + 2) + (long long)p * (nn + 4);
     const int a = (int)P[nn + 1], b = (int)P[nn + 2];
-    const double logt = log(P[nn]);
+    const double cab = P[nn + 3];       // log t + (log sf2_a - log c_a) + (log sf2_b - log c_b), from determinants of I + small
     const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     for (int idx = tid; idx < Nx * 64; idx += 256) {
@@ -1333,7 +1356,8 @@ em_pair_kernel(int N, int Nx, int Ny, const double* __restrict__ EMP,
                 // the reference's  t beta^T Q beta - mean_a mean_b  (:412,416) term by term, before the sums cancel
                 const double la = LQ[(long long)a * ldn + i], lb = LQ[(long long)b * ldn + j];
                 const double wgt = (alpha[(long long)a * sal + i] * exp(la)) * (alpha[(long long)b * sal + j] * exp(lb));
-                s = fma(wgt, expm1(logt + lq - la - lb), s);
+                // the exponent is assembled from its small parts only (never as a difference of O(10) logarithms)
+                s = fma(wgt, expm1(cab + E2[(long long)p * ldn + i] + F2[(long long)p * ldn + j] + 2.0 * acc[r][c]), s);
             }
         }
     }
@@ -1417,7 +1441,7 @@ __global__ void em_finalize_kernel(int Nx, int Ny, int npairs, const double* __r
     }
     __syncthreads();
     if (tid < npairs) {
-        const double* P = EMP + (long long)Ny * (nn + 1) + (long long)tid * (nn + 3);
+        const double* P = EMP + (long long)Ny * (2 * nn + 2) + (long long)tid * (nn + 4);
         const int a = (int)P[nn + 1], b = (int)P[nn + 2];
         double s = 0.0;
         for (int q = 0; q < ntile2; ++q) s += part[(long long)tid * ntile2 + q];
