@@ -87,7 +87,7 @@ struct gpmpc_handle_s {
     double *dG = nullptr, *dZ = nullptr, *dSigma = nullptr, *dMean = nullptr, *dVar = nullptr, *dJ = nullptr, *dCov = nullptr;
     double *dIn = nullptr, *dOut = nullptr;   // [Z | Sigma] and [mean | var | J | cov] slabs: one H2D + one D2H per host call
     int Hcap = 0;
-    double* hPinned = nullptr; size_t hPinnedBytes = 0;
+    double* hPinned = nullptr; double* dPinnedAlias = nullptr; size_t hPinnedBytes = 0; int opt_zero_copy = 1;
     // nlml scratch
     double *dU = nullptr, *dKinv = nullptr, *dGradPart = nullptr, *dGrad = nullptr;
     bool has_data = false, has_hyper = false, factorized = false;
@@ -480,7 +480,9 @@ static int ensure_pinned(gpmpc_handle_t h, size_t bytes)
     if (h->hPinnedBytes >= bytes) return GPMPC_OK;
     if (h->hPinned) cudaFreeHost(h->hPinned);
     h->hPinned = nullptr; h->hPinnedBytes = 0;
-    CUDA_TRY(cudaMallocHost((void**)&h->hPinned, bytes));
+    // mapped: small batches are read / written by the kernels directly (zero copy), see gpmpc_predict
+    CUDA_TRY(cudaHostAlloc((void**)&h->hPinned, bytes, cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&h->dPinnedAlias, h->hPinned, 0));
     h->hPinnedBytes = bytes;
     return GPMPC_OK;
 }
@@ -733,6 +735,7 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
         if (v < 0 || v > PSK_MAX_CTAS) { set_error(h, "predict_ctas must be in [0, %d]", PSK_MAX_CTAS); return GPMPC_ERR_ARG; }
         h->opt_predict_ctas = v; return GPMPC_OK;
     }
+    if (!strcmp(name, "zero_copy")) { h->opt_zero_copy = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "peer_timeout_s")) { h->opt_peer_timeout_s = value > 0.0 ? value : 60.0; return GPMPC_OK; }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
     if (!strcmp(name, "small_tiles")) { h->opt_small_tiles = (int)value; return GPMPC_OK; }
@@ -839,13 +842,13 @@ static cudaError_t psk_launch(int bm, const PredictParams& p, const double* A, l
     }
 }
 
-// persistent grid: 2 CTAs per SM, but never fewer than 12 k-steps per CTA (small N: a CTA's fixed cost -- barrier
-// init, descriptor fetch, pipeline fill -- is worth about 8 steps)
+// persistent grid: 2 CTAs per SM, but never fewer than 4 k-steps per CTA (measured at N=1000, 6 outputs: 296 CTAs of
+// 6 steps beat 144 of 12 -- the fixed cost per CTA overlaps across SMs, the steps do not)
 static int psk_grid(gpmpc_handle_t h, long long G)
 {
     int ctas = h->opt_predict_ctas > 0 ? h->opt_predict_ctas : h->psk_ctas;
     ctas = std::min(ctas, PSK_MAX_CTAS);
-    const long long by_work = std::max(1LL, G / 12);
+    const long long by_work = std::max(1LL, G / 4);
     return (int)std::min<long long>(ctas, h->opt_predict_ctas > 0 ? G : by_work);
 }
 
@@ -1249,12 +1252,22 @@ extern "C" int gpmpc_predict(gpmpc_handle_t h, int method, int H, const double* 
     double* pin = h->hPinned;
     memcpy(pin, Z, nz * 8);
     if (ns) memcpy(pin + cap * Nx, Sigma, ns * 8);
-    CUDA_TRY(cudaMemcpyAsync(h->dIn, pin, in_span * 8, cudaMemcpyHostToDevice, h->st));
-    rc = predict_core(h, method, H, h->dZ, h->dSigma, spp, mean ? h->dMean : nullptr, var ? h->dVar : nullptr,
-                      cov ? h->dCov : nullptr, jac ? h->dJ : nullptr);
-    if (rc) return rc;
+    // Small batches skip both copy operations: the ks kernel reads Z / Sigma from the mapped pinned buffer
+    // (each of its CTAs reads HG x Nx doubles once: only worthwhile while that re-read volume is small) and the
+    // assembling CTA writes mean / var / J / cov straight into it (posted writes, visible after the stream sync).
+    const int np_ = h->Npad;
+    const long long ks_ctas = (long long)((np_ + ks_chunk(h) - 1) / ks_chunk(h)) * ((std::min(H, HB) + 7) / 8 * 8) * h->nloc;
+    const bool zc_in = h->opt_zero_copy && H <= HB && ks_ctas * Nx * 8 <= 256 * 1024 && in_span * 8 <= 64 * 1024;
+    const bool zc_out = h->opt_zero_copy && out_span * 8 <= 1024 * 1024;
     double* po = pin + in_span;
-    if (out_span) CUDA_TRY(cudaMemcpyAsync(po, h->dOut + lo, out_span * 8, cudaMemcpyDeviceToHost, h->st));
+    const double* dZ_ = h->dZ; const double* dS_ = h->dSigma;
+    if (zc_in) { dZ_ = h->dPinnedAlias; dS_ = h->dPinnedAlias + cap * Nx; }
+    else CUDA_TRY(cudaMemcpyAsync(h->dIn, pin, in_span * 8, cudaMemcpyHostToDevice, h->st));
+    auto fld = [&](size_t off) { return zc_out ? h->dPinnedAlias + in_span + (off - lo) : h->dOut + off; };
+    rc = predict_core(h, method, H, dZ_, dS_, spp, mean ? fld(0) : nullptr, var ? fld(off_var) : nullptr,
+                      cov ? fld(off_c) : nullptr, jac ? fld(off_j) : nullptr);
+    if (rc) return rc;
+    if (out_span && !zc_out) CUDA_TRY(cudaMemcpyAsync(po, h->dOut + lo, out_span * 8, cudaMemcpyDeviceToHost, h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
     { int prc = peer_status_check(h); if (prc) return prc; }
     if (mean) memcpy(mean, po + (0 - lo), nm * 8);
