@@ -144,8 +144,9 @@ def run_reference(args, wl, rank):
     threads, at the SAME configuration as the GPU arm: every one of the Ny outputs is
     factorised on the CPU (set-up, not timed -- as in the GPU arm) and every timed step
     predicts all H points for all Ny outputs (ks, mean, L\\ks, var, Jacobian, TA covariance).
-    Falls back to a stated sub-sample (1 output, time x Ny) only when the host cannot hold
-    Ny factors or one CPU factorisation takes longer than 60 s."""
+    When all Ny outputs do not fit the ~150 s budget (N=16384: ~25 s of CPU set-up and ~1.3 s per predict pass
+    per output on 128 cores) a stated subset of the outputs is run at FULL N and H and the step time is scaled by
+    Ny / n (outputs are independent and cost the same): no extrapolation in N."""
     if rank != 0:
         return
     from oracle import gp_oracle as orc
@@ -158,15 +159,20 @@ def run_reference(args, wl, rank):
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 64e9
-    n_fac = Ny if avail > (Ny + 3) * 8.0 * N * N else 1
+    # bounded sample (the whole run must end within a few minutes): as many of the Ny outputs as fit a ~150 s
+    # budget, measured on the first one -- CPU factorisation (set-up, not timed) + (warmup + steps) predict passes
+    budget_s = float(os.environ.get('GPMPC_REF_BUDGET_S', '150'))
     facs = []
     t0 = time.perf_counter()
-    for a in range(n_fac):
-        t1 = time.perf_counter()
+    facs.append(orc.factor_large(w['X'], w['Y'][:, 0], w['hyper'][0]))
+    t_fac1 = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    cpu_predict_port(orc, w['X'], w['hyper'][0], facs[0]['alpha'], facs[0]['chol'], w['Z'])
+    t_pred1 = time.perf_counter() - t1
+    per_output = t_fac1 + (args.warmup + args.steps) * t_pred1
+    n_fac = int(max(1, min(Ny, budget_s // max(per_output, 1e-9), (avail // (8.0 * N * N)) - 3)))
+    for a in range(1, n_fac):
         facs.append(orc.factor_large(w['X'], w['Y'][:, a], w['hyper'][a]))
-        if a == 0 and time.perf_counter() - t1 > 60.0:
-            break
-    n_fac = len(facs)
     t_setup = time.perf_counter() - t0
 
     def step():
@@ -367,6 +373,16 @@ def main():
         sustained = {'tflops': 2 * 8192.0 ** 3 * n_it / (e0.elapsed_time(e1) * 1e-3) / 1e12, 'iters': n_it,
                      'seconds': e0.elapsed_time(e1) * 1e-3, 'clocks': ck}
     del a, bmat
+    # write-only HBM bandwidth (the K build only writes): best of 5 fills of a 2 GiB buffer, for context beside the
+    # copy-bandwidth denominator of MEASURED_PEAKS.json
+    wbuf = torch.empty(1 << 28, dtype=torch.float64, device='cuda')
+    wbest = 1e9
+    for _ in range(5):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); wbuf.fill_(1.0); e1.record(); torch.cuda.synchronize()
+        wbest = min(wbest, e0.elapsed_time(e1))
+    hbm_write_gbs = wbuf.numel() * 8 / wbest / 1e6
+    del wbuf
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -400,6 +416,7 @@ def main():
             'kbuild_full': {'ms': sec['kbuild_full_ms'], 'gbs': 8.0 * Np * Np / sec['kbuild_full_ms'] / 1e6,
                             'frac': 8.0 * Np * Np / sec['kbuild_full_ms'] / 1e6 / hbm_peak, 'bound': 'hbm',
                             'algorithmic_bytes': 8.0 * Np * Np, 'traffic': tj.get('kbuild_full_N16384_bytes') if N == 16384 else None,
+                            'write_only_peak_gbs': hbm_write_gbs, 'frac_of_write_only_peak': 8.0 * Np * Np / sec['kbuild_full_ms'] / 1e6 / hbm_write_gbs,
                             'peak_source': hbm_src},
             'kbuild_lower': {'ms': sec['kbuild_lower_ms'], 'gbs': 4.0 * Np * (Np + 1) / sec['kbuild_lower_ms'] / 1e6,
                              'frac': 4.0 * Np * (Np + 1) / sec['kbuild_lower_ms'] / 1e6 / hbm_peak, 'bound': 'hbm',

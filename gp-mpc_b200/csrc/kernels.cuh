@@ -539,10 +539,11 @@ leaf_potrf_trtri_v2_kernel(double* __restrict__ A, int lda, long long sA,
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double rsqrt_seeded(double d)
 {
-    // MUFU.RSQ (fp32, ~2^-22) + two Newton steps in fp64: relative error ~1e-15; arguments outside
-    // fp32's comfortable range take the library routine
-    if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
-    double y = (double)rsqrtf((float)d);
+    // rsqrt.approx.f64 (SASS MUFU.RSQ64H on the high word, ~2^-22, no fp32 round trip) + two Newton steps in
+    // fp64: relative error ~1e-15; tiny / huge / non-positive arguments take the library routine
+    if (!(d > 1e-290 && d < 1e290)) return rsqrt(d);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
     double e = fma(-(d * y), y, 1.0);
     y = fma(0.5 * y, e, y);
     e = fma(-(d * y), y, 1.0);
