@@ -189,7 +189,8 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
         if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {
             CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_N * LEAF_LD * 8));
             CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_DOUBLES * 8));
-            CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF3_SMEM_DOUBLES * 8));
+            CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF3_SMEM_DOUBLES * 8));
+            CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF3_SMEM_DOUBLES * 8));
             conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
         }
         if (h->opt_leaf_variant == 0)
@@ -198,9 +199,12 @@ static int potrf_inv_rec(gpmpc_handle_t h, double* A, double* Li, long long sA, 
         else if (h->opt_leaf_variant == 1)
             leaf_potrf_trtri_v2_kernel<<<batch, 256, LF_SMEM_DOUBLES * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
                                                                                 Li + (long long)off * ld + off, ld, sLi, dInfo, off);
-        else
-            leaf_potrf_trtri_v3_kernel<<<batch, 256, LF3_SMEM_DOUBLES * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
-                                                                                 Li + (long long)off * ld + off, ld, sLi, dInfo, off);
+        else if (h->opt_leaf_variant == 2)
+            leaf_potrf_trtri_v3_kernel<false><<<batch, 256, LF3_SMEM_DOUBLES * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
+                                                                                        Li + (long long)off * ld + off, ld, sLi, dInfo, off);
+        else       // 3: v3 with two pivots per step
+            leaf_potrf_trtri_v3_kernel<true><<<batch, 256, LF3_SMEM_DOUBLES * 8, h->st>>>(A + (long long)off * ld + off, ld, sA,
+                                                                                       Li + (long long)off * ld + off, ld, sLi, dInfo, off);
         CUDA_TRY(cudaGetLastError());
         return GPMPC_OK;
     }

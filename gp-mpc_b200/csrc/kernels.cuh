@@ -584,6 +584,59 @@ __device__ __forceinline__ void warp_potrf16(double* D, double* ipd, int* info, 
     __syncwarp();
 }
 
+// Same contract, TWO columns per step: the pivots' reciprocal square roots are the longest dependent chain
+// of the whole factorisation (~9 dependent fp64 operations at ~40 cycles each per pivot).  For columns
+// j, j+1 with Schur-complement entries p = S_jj, q = S_j+1,j, r = S_j+1,j+1 the second pivot is
+// s = r - q^2/p = det/p with det = p r - q^2, so  1/sqrt(s) = rsqrt(det) * sqrt(p):  rsqrt(p) and rsqrt(det)
+// are independent and run concurrently -- 11 dependent operations per two pivots instead of 18.  Arithmetic is
+// the standard Cholesky recurrence (same stability: s inherits the relative error eps p r / det either way).
+__device__ __forceinline__ void warp_potrf16x2(double* D, double* ipd, int* info, int info_val0, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const int r = lane & 15;
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = D[r * LF_LD + k];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        const double p = __shfl_sync(full, a[j], j);
+        const double q = __shfl_sync(full, a[j], j + 1);
+        const double rr = __shfl_sync(full, a[j + 1], j + 1);
+        const double det = fma(p, rr, -(q * q));
+        if (lane == 0) {
+            if (!(p > 0.0)) atomicCAS(info, 0, info_val0 + j + 1);
+            else if (!(det > 0.0)) atomicCAS(info, 0, info_val0 + j + 2);
+        }
+        double yp = rsqrt_seeded(p), yd = rsqrt_seeded(det);            // independent chains
+        double sp = p * yp;
+        sp = fma(fma(-sp, sp, p), 0.5 * yp, sp);                         // sqrt(p)
+        if (!(p > 0.0)) { sp = sqrt(p); yp = 1.0 / sp; }
+        const double c21 = q * yp;                                       // L[j+1][j]
+        double ys = yd * sp;                                             // 1 / sqrt(s)
+        const double s2 = fma(-c21, c21, rr);                            // s by the standard formula: diagonal entry only (off the chain)
+        double ss = s2 * ys;
+        ss = fma(fma(-ss, ss, s2), 0.5 * ys, ss);                        // sqrt(s)
+        if (!(det > 0.0) || !(p > 0.0)) { ss = sqrt(s2); ys = 1.0 / ss; }
+        const double lj = (r == j) ? sp : a[j] * yp;                     // column j
+        const double t = fma(-lj, c21, a[j + 1]);
+        const double lj1 = (r == j + 1) ? ss : t * ys;                   // column j+1 (row j: above the diagonal, never read)
+        a[j] = lj; a[j + 1] = lj1;
+        if (lane == 0) { ipd[j] = yp; ipd[j + 1] = ys; }
+#pragma unroll
+        for (int k = j + 2; k < 16; ++k) {
+            const double lkj = __shfl_sync(full, lj, k);
+            const double lkj1 = __shfl_sync(full, lj1, k);
+            a[k] = fma(-lj1, lkj1, fma(-lj, lkj, a[k]));               // meaningful for r >= k
+        }
+    }
+    __syncwarp();
+    if (lane < 16) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (k <= r) D[r * LF_LD + k] = a[k];
+    }
+    __syncwarp();
+}
+
 // inverse of a factorised 16x16 block (off the critical path): lane r computes column r by forward
 // substitution; two partial sums shorten the dependent FMA chain
 __device__ __forceinline__ void warp_trtri16(const double* D, const double* ipd, double* Dinv, int lane)
@@ -605,6 +658,7 @@ __device__ __forceinline__ void warp_trtri16(const double* D, const double* ipd,
 }
 
 #define LF3_SMEM_DOUBLES (LEAF_N * LF_LD + 8 * 16 * 17 + 8 * 16 + 64 * 68 + 64)
+template <bool TWOCOL>
 __global__ void __launch_bounds__(256, 1)
 leaf_potrf_trtri_v3_kernel(double* __restrict__ A, int lda, long long sA,
                            double* __restrict__ Li, int ldi, long long sLi,
@@ -666,7 +720,10 @@ leaf_potrf_trtri_v3_kernel(double* __restrict__ A, int lda, long long sA,
         for (int kk = 0; kk < 4; ++kk) dmma884(acc0, acc1, -pa[kk * 4], pb[kk * 4]);
         cp[0] = acc0; cp[1] = acc1;
     };
-    if (warp == 0) warp_potrf16(S, ipdAll, info + blockIdx.x, info_base, lane);
+    if (warp == 0) {
+        if (TWOCOL) warp_potrf16x2(S, ipdAll, info + blockIdx.x, info_base, lane);
+        else warp_potrf16(S, ipdAll, info + blockIdx.x, info_base, lane);
+    }
     __syncthreads();
     panel(0, ipdAll);
     __syncthreads();
@@ -681,7 +738,8 @@ leaf_potrf_trtri_v3_kernel(double* __restrict__ A, int lda, long long sA,
         }
         __syncthreads();
         if (warp == 0) {
-            warp_potrf16(S + b0 * LF_LD + b0, ipdAll + (kb + 1) * 16, info + blockIdx.x, info_base + b0, lane);
+            if (TWOCOL) warp_potrf16x2(S + b0 * LF_LD + b0, ipdAll + (kb + 1) * 16, info + blockIdx.x, info_base + b0, lane);
+            else warp_potrf16(S + b0 * LF_LD + b0, ipdAll + (kb + 1) * 16, info + blockIdx.x, info_base + b0, lane);
         } else if (warp == 1) {
             warp_trtri16(S + c0 * LF_LD + c0, ipdAll + kb * 16, DinvAll + kb * 16 * 17, lane);
         } else {
