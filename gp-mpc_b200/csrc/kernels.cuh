@@ -1,6 +1,7 @@
 // Device kernels of the GP hot path other than the DMMA GEMM family.
 // Reference semantics are cited as file:line of helgeanl/GP-MPC.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 // hyper layout per output (device copy): [ell_0..ell_{Nx-1}, sf, sn]  (gp_class.py:139-142)
@@ -194,50 +195,66 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
     // tiles that touch the diagonal or the identity tail take the checked epilogue
     const bool special = !offdiag || (i0 + KB2_TILE > N) || (j0 + KB2_TILE > N);
     const int nk4 = KD >> 2;
+    // SP = tile touches the diagonal or the identity tail (checked epilogue, upper clamp); MR = mirrored tile stored too.
+    // Both are CTA-uniform: one branch per CTA picks the instantiation, the hot path carries neither the checks nor
+    // fmin/fmax (their NaN semantics cost ~7 instructions each on this target; a plain compare-select is 3).
+    auto tile_body = [&](auto sp_tag, auto mr_tag) {
+        constexpr bool SP = decltype(sp_tag)::value, MR = decltype(mr_tag)::value;
 #pragma unroll 1
-    for (int mi = 0; mi < 2; ++mi) {
-        const int rl = warp * 16 + mi * 8 + g;            // local row of this lane's accumulators
-        const int row = i0 + rl;
-        const double* ua = Ui + rl * S + t;
-        const double qr = qi[rl];
-        double* drow = Ka + (long long)row * ld + j0 + 2 * t;              // direct:  K[row][j0 + cl]
-        double* mcol = Ka + (long long)(j0 + 2 * t) * ld + row;            // mirror:  K[j0 + cl][row]
+        for (int mi = 0; mi < 2; ++mi) {
+            const int rl = warp * 16 + mi * 8 + g;            // local row of this lane's accumulators
+            const int row = i0 + rl;
+            const double* ua = Ui + rl * S + t;
+            const double qr = qi[rl];
+            double* drow = Ka + (long long)row * ld + j0 + 2 * t;              // direct:  K[row][j0 + cl]
+            double* mcol = Ka + (long long)(j0 + 2 * t) * ld + row;            // mirror:  K[j0 + cl][row]
 #pragma unroll 1
-        for (int ng = 0; ng < 4; ++ng) {
-            double acc[4][2];
+            for (int ng = 0; ng < 4; ++ng) {
+                double acc[4][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
-            const double* ub = Uj + (ng * 32 + g) * S + t;
-            for (int kk = 0; kk < nk4; ++kk) {
-                const double av = ua[kk * 4];
+                for (int q = 0; q < 4; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+                const double* ub = Uj + (ng * 32 + g) * S + t;
+                for (int kk = 0; kk < nk4; ++kk) {
+                    const double av = ua[kk * 4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) dmma884(acc[q][0], acc[q][1], av, ub[q * 8 * S + kk * 4]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int cl0 = ng * 32 + q * 8;          // + 2t folded into the base pointers
-                const double2 qc = *reinterpret_cast<const double2*>(qj + cl0 + 2 * t);
-                // log2 k, clamped from below (far-apart points under tiny length scales: SLSQP probes them); the upper clamp
-                // (k <= sf2 despite rounding) only matters where the distance is 0, i.e. on diagonal tiles
-                double t0 = fmax((qr + qc.x) + acc[q][0], -1020.0), t1 = fmax((qr + qc.y) + acc[q][1], -1020.0);   // 2^-1020 ~ 0
-                if (special) { t0 = fmin(t0, l2sf2); t1 = fmin(t1, l2sf2); }
-                double v0 = FULL ? exp2_t16(t0, T256) : exp2_t256(t0, T256);
-                double v1 = FULL ? exp2_t16(t1, T256) : exp2_t256(t1, T256);
-                if (special) {
-                    const int col = j0 + cl0 + 2 * t;
-                    if (row == col) v0 += dg;
-                    if (row == col + 1) v1 += dg;
-                    if (row >= N || col >= N) v0 = (row == col) ? 1.0 : 0.0;
-                    if (row >= N || col + 1 >= N) v1 = (row == col + 1) ? 1.0 : 0.0;
+                    for (int q = 0; q < 4; ++q) dmma884(acc[q][0], acc[q][1], av, ub[q * 8 * S + kk * 4]);
                 }
-                *reinterpret_cast<double2*>(drow + cl0) = make_double2(v0, v1);
-                if (mirror) {
-                    double* m = mcol + (long long)cl0 * ld;
-                    m[0] = v0;
-                    m[ld] = v1;
+                double* mrow = mcol + (long long)(ng * 32) * ld;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cl0 = ng * 32 + q * 8;          // + 2t folded into the base pointers
+                    const double2 qc = *reinterpret_cast<const double2*>(qj + cl0 + 2 * t);
+                    // log2 k, clamped from below (far-apart points under tiny length scales: SLSQP probes them; 2^-1020 ~ 0)
+                    double t0 = (qr + qc.x) + acc[q][0], t1 = (qr + qc.y) + acc[q][1];
+                    t0 = (t0 < -1020.0) ? -1020.0 : t0;
+                    t1 = (t1 < -1020.0) ? -1020.0 : t1;
+                    if (SP) {                                 // k <= sf2 despite rounding: only where the distance can be 0
+                        t0 = (t0 > l2sf2) ? l2sf2 : t0;
+                        t1 = (t1 > l2sf2) ? l2sf2 : t1;
+                    }
+                    double v0 = FULL ? exp2_t16(t0, T256) : exp2_t256(t0, T256);
+                    double v1 = FULL ? exp2_t16(t1, T256) : exp2_t256(t1, T256);
+                    if (SP) {
+                        const int col = j0 + cl0 + 2 * t;
+                        if (row == col) v0 += dg;
+                        if (row == col + 1) v1 += dg;
+                        if (row >= N || col >= N) v0 = (row == col) ? 1.0 : 0.0;
+                        if (row >= N || col + 1 >= N) v1 = (row == col + 1) ? 1.0 : 0.0;
+                    }
+                    *reinterpret_cast<double2*>(drow + cl0) = make_double2(v0, v1);
+                    if (MR) {
+                        mrow[0] = v0;
+                        mrow[ld] = v1;
+                        mrow += 8 * (long long)ld;
+                    }
                 }
             }
         }
+    };
+    if (special) {
+        if (mirror) tile_body(std::true_type{}, std::true_type{}); else tile_body(std::true_type{}, std::false_type{});
+    } else {
+        if (mirror) tile_body(std::false_type{}, std::true_type{}); else tile_body(std::false_type{}, std::false_type{});
     }
 }
 

@@ -25,7 +25,7 @@ for N in [int(a) for a in sys.argv[1:]] or [1024, 4096, 8192, 16384]:
     eng = gp_mpc_b200.Engine(N, 10, 1, device=0)
     eng.set_data(pp['X'], pp['Y']); eng.set_hyper(pp['hyper'])
     n1 = (N // 128 // 2) * 128; n2 = N - n1
-    for name, vals in (('gemm_variant', (1, 3)), ('leaf_variant', (1, 2, 3)), ('overlap', (0, 1))):
+    for name, vals in (('gemm_variant', (1, 3)), ('leaf_variant', (1, 2, 3)), ('overlap', (0, 1)), ('lookahead', (0, 1)), ('lookahead_min', (512, 2048, 1024))):
         for v in vals:
             eng.set_option(name, v)
             ms = eng.profile(L.PROF_SYRK, reps=3); msf = eng.profile(L.PROF_FACTORIZE, reps=3)
