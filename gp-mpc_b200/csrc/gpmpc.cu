@@ -907,7 +907,7 @@ static void psk_base(gpmpc_handle_t h, PredictParams& p, int Hc)
 // Small problems (Npad <= 4096) take 256-point chunks and 2 rows per CTA: there the kernel is latency-bound
 // and needs CTAs, not L2 savings.
 static inline bool ks_small(gpmpc_handle_t h) { return h->Npad <= 4096; }
-static inline int ks_chunk(gpmpc_handle_t h) { return ks_small(h) ? 256 : (h->Nx <= 12 ? 1024 : (h->Nx <= 24 ? 512 : 256)); }
+static inline int ks_chunk(gpmpc_handle_t h) { return ks_small(h) ? 256 : (h->Nx <= 24 ? 512 : 256); }
 
 template <int NXP, int CH, int HG>
 static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
@@ -937,9 +937,9 @@ static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, in
         if (Nx <= 24) return launch_ks<24, 256, 2>(h, dZc, Hc, bm, nblk);
         return launch_ks<32, 256, 2>(h, dZc, Hc, bm, nblk);
     }
-    if (Nx <= 4) return launch_ks<4, 1024, 8>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 8) return launch_ks<8, 1024, 8>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 12) return launch_ks<12, 1024, 8>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 4) return launch_ks<4, 512, 8>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 8) return launch_ks<8, 512, 8>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 12) return launch_ks<12, 512, 8>(h, dZc, Hc, bm, nblk);
     if (Nx <= 16) return launch_ks<16, 512, 8>(h, dZc, Hc, bm, nblk);
     if (Nx <= 24) return launch_ks<24, 512, 8>(h, dZc, Hc, bm, nblk);
     return launch_ks<32, 256, 8>(h, dZc, Hc, bm, nblk);

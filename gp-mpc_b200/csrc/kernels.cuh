@@ -219,7 +219,6 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
 #pragma unroll
                     for (int q = 0; q < 4; ++q) dmma884(acc[q][0], acc[q][1], av, ub[q * 8 * S + kk * 4]);
                 }
-                double* mrow = mcol + (long long)(ng * 32) * ld;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int cl0 = ng * 32 + q * 8;          // + 2t folded into the base pointers
@@ -243,9 +242,9 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
                     }
                     *reinterpret_cast<double2*>(drow + cl0) = make_double2(v0, v1);
                     if (MR) {
-                        mrow[0] = v0;
-                        mrow[ld] = v1;
-                        mrow += 8 * (long long)ld;
+                        double* m = mcol + (long long)cl0 * ld;        // independent address per store pair (no serial pointer chain)
+                        m[0] = v0;
+                        m[ld] = v1;
                     }
                 }
             }
@@ -1036,7 +1035,7 @@ ks_rows_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
 {
     extern __shared__ double Xs[];                         // [Nx][CH]
     __shared__ double red[8][NXP + 1];
-    __shared__ double zs[HG][NXP], ie[NXP], ie2[NXP];
+    __shared__ double zs[HG][NXP], ie[NXP], ie2[NXP], T16s[16], l2sf2_s;
     // let the dependent product kernel start launching once every CTA of this grid is resident (it waits
     // for this grid's completion before reading KS^T): hides its launch latency and prologue
     asm volatile("griddepcontrol.launch_dependents;");
@@ -1052,12 +1051,14 @@ ks_rows_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
         ie[tid] = 1.0 / e;
         ie2[tid] = 1.0 / (e * e);
     }
+    if (tid >= 64 && tid < 80) T16s[tid - 64] = c_exp2_tab[tid - 64];
+    if (tid == 96) l2sf2_s = 2.0 * log2(fabs(hp[Nx]));
     for (int idx = tid; idx < HG * NXP; idx += 256) {
         const int r = idx / NXP, d = idx - r * NXP, h = hg * HG + r;
         zs[r][d] = (d < Nx && h < H) ? Z[(long long)h * Nx + d] : 0.0;
     }
     __syncthreads();
-    const double sf2 = hp[Nx] * hp[Nx];
+    const double l2sf2 = l2sf2_s;
     const double* al = alpha + (long long)a * sal;
     double alv[CH / 256];
 #pragma unroll
@@ -1089,7 +1090,11 @@ ks_rows_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
                         dist = fma(sc, sc, dist);
                     }
                 }
-                ks = sf2 * exp(-0.5 * dist);
+                // sf2 exp(-dist/2) = 2^(log2 sf2 - log2(e)/2 dist) with the table exp2 of the K build (~2 ulp, half the
+                // instructions of the library exp)
+                double te = fma(-0.72134752044448170, dist, l2sf2);
+                te = (te < -1020.0) ? -1020.0 : te;
+                ks = exp2_t16(te, T16s);
                 const double w = alv[q] * ks;
                 am += w;
 #pragma unroll
