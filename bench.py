@@ -424,7 +424,7 @@ def main():
             'syrk_trailing_update': {'ms': sec['syrk_ms'], 'tflops': syrk_flops / sec['syrk_ms'] / 1e9,
                                      'frac': syrk_flops / sec['syrk_ms'] / 1e9 / dgemm_tf, 'bound': 'tensor',
                                      'shape': 'C(%d x %d lower) -= P P^T, K=%d' % (n2, n2, n1),
-                                     'traffic': tj.get('syrk_N16384_bytes') if N == 16384 else None},
+                                     'traffic': tj.get('syrk_8192x8192_K8192_bytes') if N == 16384 else None},
             'factorize_potrf_trtri': {'ms': sec['factorize_ms'], 'tflops': (2.0 / 3.0) * float(Np) ** 3 / sec['factorize_ms'] / 1e9,
                                       'frac': (2.0 / 3.0) * float(Np) ** 3 / sec['factorize_ms'] / 1e9 / dgemm_tf, 'bound': 'tensor',
                                       'note': 'K build + potrf + explicit L^-1 of one output, 2N^3/3 flops'},

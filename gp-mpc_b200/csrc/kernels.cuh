@@ -135,6 +135,9 @@ __device__ __forceinline__ double exp2_t16(double t, const double* __restrict__ 
     return __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));
 }
 
+struct KbTrue { __device__ constexpr operator bool() const { return true; } };
+struct KbFalse { __device__ constexpr operator bool() const { return false; } };
+
 #define KB2_TILE 128
 template <bool FULL>
 __global__ void __launch_bounds__(256)
@@ -196,10 +199,10 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
     const bool special = !offdiag || (i0 + KB2_TILE > N) || (j0 + KB2_TILE > N);
     const int nk4 = KD >> 2;
     // SP = tile touches the diagonal or the identity tail (checked epilogue, upper clamp); MR = mirrored tile stored too.
-    // Both are CTA-uniform: one branch per CTA picks the instantiation, the hot path carries neither the checks nor
-    // fmin/fmax (their NaN semantics cost ~7 instructions each on this target; a plain compare-select is 3).
+    // Both are CTA-uniform.  No fmin/fmax anywhere (their NaN semantics cost ~7 instructions each on this target; a plain
+    // compare-select is 3).
     auto tile_body = [&](auto sp_tag, auto mr_tag) {
-        constexpr bool SP = decltype(sp_tag)::value, MR = decltype(mr_tag)::value;
+        const bool SP = sp_tag, MR = mr_tag;      // KbTrue / KbFalse fold at compile time, plain bools stay run-time
 #pragma unroll 1
         for (int mi = 0; mi < 2; ++mi) {
             const int rl = warp * 16 + mi * 8 + g;            // local row of this lane's accumulators
@@ -250,10 +253,14 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
             }
         }
     };
-    if (special) {
-        if (mirror) tile_body(std::true_type{}, std::true_type{}); else tile_body(std::true_type{}, std::false_type{});
+    if (FULL) {
+        // store-bound: one body with run-time flags (four specialised copies measured 5 % slower: CTAs of different kinds
+        // share an SM and the instruction working set quadruples)
+        tile_body(special, mirror);
+    } else if (special) {
+        tile_body(KbTrue{}, KbFalse{});
     } else {
-        if (mirror) tile_body(std::false_type{}, std::true_type{}); else tile_body(std::false_type{}, std::false_type{});
+        tile_body(KbFalse{}, KbFalse{});      // instruction-bound: the hot path carries no checks at all
     }
 }
 
