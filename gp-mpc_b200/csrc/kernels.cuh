@@ -135,6 +135,30 @@ __device__ __forceinline__ double exp2_t16(double t, const double* __restrict__ 
     return __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));
 }
 
+// Two-level table: 2^t = 2^e * T1[(n >> 4) & 15] * T2[n & 15] * 2^f with n = rint(256 t), T1[k] = 2^(k/16), T2[m] = 2^(m/256),
+// |f| <= 1/512 (degree-4 polynomial, truncation 3.8e-17).  Both tables have ONE entry per shared-memory bank, so the
+// lookups are conflict-free whatever the lane pattern (the flat 256-entry table replays ~3x), and the polynomial needs four
+// coefficients instead of seven (each costs two UMOVs in the loop on this target).  ~2.2 ulp.
+__constant__ double c_exp2_tab2[16] = {
+    1, 1.0027112750502025, 1.0054299011128027, 1.0081558981184175, 1.0108892860517005, 1.0136300849514894,
+    1.0163783149109531, 1.0191339960777379, 1.0218971486541166, 1.0246677928971357, 1.0274459491187637,
+    1.030231637686041, 1.0330248790212284, 1.0358256936019572, 1.0386341019613787, 1.0414501246883161};
+__device__ __forceinline__ double exp2_t2lvl(double t, const double* __restrict__ T32)
+{
+    const double SH = 6755399441055744.0;            // 1.5 * 2^52: rint(256 t) lands in the low word
+    const double s = fma(t, 256.0, SH);
+    const int n = __double2loint(s);
+    const double f = fma(s - SH, -0.00390625, t);    // |f| <= 1/512, exact
+    double p = 0.009618129107628477;                 // (ln 2)^k / k!, k = 4..1
+    p = fma(p, f, 0.05550410866482158);
+    p = fma(p, f, 0.24022650695910072);
+    p = fma(p, f, 0.6931471805599453);
+    p = fma(p, f, 1.0);
+    p *= T32[(n >> 4) & 15];
+    p *= T32[16 + (n & 15)];
+    return __hiloint2double(__double2hiint(p) + ((n >> 8) << 20), __double2loint(p));
+}
+
 struct KbTrue { __device__ constexpr operator bool() const { return true; } };
 struct KbFalse { __device__ constexpr operator bool() const { return false; } };
 
@@ -171,10 +195,9 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
         sc[tid] = (tid < Nx) ? 1.2011224087864498 / hp[tid] : 0.0;
         mus[tid] = (tid < Nx) ? mu[tid] : 0.0;
     }
-    // the full build is store-bound: it takes the 16-entry table (one entry per shared-memory bank: conflict-free);
-    // the lower-only build is instruction-bound: 256 entries buy a degree-4 instead of a degree-7 polynomial
-    if (FULL) { if (tid < 16) T256[tid] = c_exp2_tab[tid]; }
-    else T256[tid] = c_exp2_tab256[tid];
+    // two 16-entry tables (exp2_t2lvl): conflict-free lookups and a degree-4 polynomial
+    if (tid < 16) T256[tid] = c_exp2_tab[tid];
+    else if (tid < 32) T256[tid] = c_exp2_tab2[tid - 16];
     __syncthreads();
     {   // scaled, centred coordinates of the 128 row points (tid < 128) / column points
         const int p = (tid < KB2_TILE) ? i0 + tid : j0 + tid - KB2_TILE;
@@ -234,8 +257,7 @@ kbuild_dmma_kernel(const double* __restrict__ XT, int ldx, int N, int Nx, const 
                         t0 = (t0 > l2sf2) ? l2sf2 : t0;
                         t1 = (t1 > l2sf2) ? l2sf2 : t1;
                     }
-                    double v0 = FULL ? exp2_t16(t0, T256) : exp2_t256(t0, T256);
-                    double v1 = FULL ? exp2_t16(t1, T256) : exp2_t256(t1, T256);
+                    double v0 = exp2_t2lvl(t0, T256), v1 = exp2_t2lvl(t1, T256);
                     if (SP) {
                         const int col = j0 + cl0 + 2 * t;
                         if (row == col) v0 += dg;
