@@ -215,7 +215,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if os.environ.get('GPMPC_BENCH_NY'):          # diagnostics: e.g. one output per GPU on fewer GPUs
+        wl['Ny'] = int(os.environ['GPMPC_BENCH_NY']); wl['name'] += ' [Ny=%d override]' % wl['Ny']
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

@@ -937,6 +937,15 @@ static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, in
         if (Nx <= 24) return launch_ks<24, 256, 2>(h, dZc, Hc, bm, nblk);
         return launch_ks<32, 256, 2>(h, dZc, Hc, bm, nblk);
     }
+    // few outputs: 2 rows per CTA (the grid needs CTAs more than L2 savings: 224 CTAs of 8 rows took 27 us at one output)
+    if ((long long)nblk * ((bm + 7) / 8) * h->nloc < 1000) {
+        if (Nx <= 4) return launch_ks<4, 512, 2>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 8) return launch_ks<8, 512, 2>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 12) return launch_ks<12, 512, 2>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 16) return launch_ks<16, 512, 2>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 24) return launch_ks<24, 512, 2>(h, dZc, Hc, bm, nblk);
+        return launch_ks<32, 256, 2>(h, dZc, Hc, bm, nblk);
+    }
     if (Nx <= 4) return launch_ks<4, 512, 8>(h, dZc, Hc, bm, nblk);
     if (Nx <= 8) return launch_ks<8, 512, 8>(h, dZc, Hc, bm, nblk);
     if (Nx <= 12) return launch_ks<12, 512, 8>(h, dZc, Hc, bm, nblk);

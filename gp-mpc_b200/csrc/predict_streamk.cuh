@@ -210,31 +210,36 @@ __device__ __forceinline__ void psk_iter_next(PskIter& it, int nt)
     }
 }
 
-// [mean, var, J_0..] records of output a for the chunk's test points (one warp per point):
-//   mean, J from the partial sums of ks_mean_jac_kernel; var = sf2 - sum_jt SQ (gp_functions.py:125-126,136)
-__device__ __forceinline__ void psk_finalize_output(const PredictParams& p, int a, int warp, int nwarps, int lane)
+// [mean, var, J_0..] records of output a for the chunk's test points.  Flat over (point, field): every thread owns
+// one record field at a time and sums its partials in fixed order (deterministic); one warp per point with a
+// serial loop over the partial blocks took 14 us here at one output (50 points x 32 blocks x 11 fields).
+//   mean, J from the partial sums of ks_rows_kernel; var = sf2 - sum_jt SQ (gp_functions.py:125-126,136)
+__device__ __forceinline__ void psk_finalize_output(const PredictParams& p, int a, int tid, int nth)
 {
-    const int Nx = p.Nx;
-    for (int h = warp; h < p.Hc; h += nwarps) {
-        const double* sq = p.SQ + ((long long)a * 64 + h) * p.nt;
-        double sv = 0.0;
-        for (int j = lane; j < p.nt; j += 32) sv += __ldcg(sq + j);
-        sv = warp_sum(sv);
-        const long long off = (((long long)(p.slot0 + a)) * p.Htot + p.h0 + h) * (Nx + 2);
-        auto put = [&](int d, double v) {
-            if (!p.use_peers) { p.Gloc[off + d] = v; return; }
-            for (int r = 0; r < p.pa.world; ++r) p.pa.base[r][p.pa.goff + off + d] = v;
-        };
-        for (int q = lane; q <= Nx; q += 32) {                 // q = 0: mean, q >= 1: J_{q-1}  (NX_MAX = 32: <= 2 rounds)
-            const double* pm = p.PMJ + (((long long)a * p.Hc + h) * p.nblk_mj) * (Nx + 1) + q;
-            double sm = 0.0;
-            for (int b = 0; b < p.nblk_mj; ++b) sm += pm[(long long)b * (Nx + 1)];
-            put(q == 0 ? 0 : q + 1, sm);
-        }
-        if (lane == 31) {
+    const int Nx = p.Nx, F = Nx + 2;
+    for (int idx = tid; idx < p.Hc * F; idx += nth) {
+        const int h = idx / F, q = idx - h * F;            // q = 0: mean, 1: var, q >= 2: J_{q-2}
+        double val;
+        if (q == 1) {
+            const double* sq = p.SQ + ((long long)a * 64 + h) * p.nt;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // four independent chains, fixed association
+            int j = 0;
+            for (; j + 4 <= p.nt; j += 4) { s0 += __ldcg(sq + j); s1 += __ldcg(sq + j + 1); s2 += __ldcg(sq + j + 2); s3 += __ldcg(sq + j + 3); }
+            for (; j < p.nt; ++j) s0 += __ldcg(sq + j);
             const double sf = p.hyp[(long long)a * p.hyp_ld + Nx];
-            put(1, sf * sf - sv);
+            val = sf * sf - ((s0 + s1) + (s2 + s3));
+        } else {
+            const int qq = (q == 0) ? 0 : q - 1;               // PMJ field: 0 = mean, d+1 = J_d
+            const double* pm = p.PMJ + (((long long)a * p.Hc + h) * p.nblk_mj) * (Nx + 1) + qq;
+            double s0 = 0.0, s1 = 0.0;
+            int b = 0;
+            for (; b + 2 <= p.nblk_mj; b += 2) { s0 += pm[(long long)b * (Nx + 1)]; s1 += pm[(long long)(b + 1) * (Nx + 1)]; }
+            if (b < p.nblk_mj) s0 += pm[(long long)b * (Nx + 1)];
+            val = s0 + s1;
         }
+        const long long off = (((long long)(p.slot0 + a)) * p.Htot + p.h0 + h) * F + q;
+        if (!p.use_peers) p.Gloc[off] = val;
+        else for (int r = 0; r < p.pa.world; ++r) p.pa.base[r][p.pa.goff + off] = val;
     }
     if (p.use_peers) __threadfence_system(); else __threadfence();
 }
@@ -287,7 +292,7 @@ finalize_kernel(const PredictParams p)
     extern __shared__ double sh[];
     __shared__ unsigned int s_flag;
     __shared__ int s_ok;
-    psk_finalize_output(p, blockIdx.x, threadIdx.x >> 5, PSK_THREADS / 32, threadIdx.x & 31);
+    psk_finalize_output(p, blockIdx.x, threadIdx.x, PSK_THREADS);
     psk_step_tail(p, sh, threadIdx.x, PSK_THREADS, &s_flag, &s_ok);
 }
 
@@ -486,7 +491,7 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
 
         // ---- this CTA completed output a: build its records; last output => publish / assemble
         __threadfence();
-        if (p.finalize) psk_finalize_output(p, a, warp, PSK_THREADS / 32, lane);
+        if (p.finalize) psk_finalize_output(p, a, tid, PSK_THREADS);
         psk_step_tail(p, smem, tid, PSK_THREADS, &s_flag, &s_ok);
     }
     if (p.dbg && threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); p.dbg[2 * blockIdx.x + 1] = t1; }
