@@ -907,16 +907,18 @@ static void psk_base(gpmpc_handle_t h, PredictParams& p, int Hc)
 // Small problems (Npad <= 4096) take 256-point chunks and 2 rows per CTA: there the kernel is latency-bound
 // and needs CTAs, not L2 savings.
 static inline bool ks_small(gpmpc_handle_t h) { return h->Npad <= 4096; }
-static inline int ks_chunk(gpmpc_handle_t h) { return ks_small(h) ? 256 : (h->Nx <= 24 ? 512 : 256); }
+// large N with few local outputs: 2048-point chunks read straight from global memory, one row per CTA (see ks_rows_kernel)
+static inline bool ks_direct(gpmpc_handle_t h) { return !ks_small(h) && (long long)h->nloc * (h->Npad / 512) * 7 < 1000; }
+static inline int ks_chunk(gpmpc_handle_t h) { return ks_small(h) ? 256 : (ks_direct(h) ? 2048 : (h->Nx <= 24 ? 512 : 256)); }
 
-template <int NXP, int CH, int HG>
+template <int NXP, int CH, int HG, bool STAGE = true>
 static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
-    auto kern = ks_rows_kernel<NXP, CH, HG>;
-    const int smem = h->Nx * CH * 8;
+    auto kern = ks_rows_kernel<NXP, CH, HG, STAGE>;
+    const int smem = STAGE ? h->Nx * CH * 8 : 0;
     static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
     if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {      // static + dynamic may pass 48 KB
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NXP * CH * 8);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE ? NXP * CH * 8 : 0);
         if (e != cudaSuccess) return e;
         conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
     }
@@ -937,14 +939,13 @@ static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, in
         if (Nx <= 24) return launch_ks<24, 256, 2>(h, dZc, Hc, bm, nblk);
         return launch_ks<32, 256, 2>(h, dZc, Hc, bm, nblk);
     }
-    // few outputs: 2 rows per CTA (the grid needs CTAs more than L2 savings: 224 CTAs of 8 rows took 27 us at one output)
-    if ((long long)nblk * ((bm + 7) / 8) * h->nloc < 1000) {
-        if (Nx <= 4) return launch_ks<4, 512, 2>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 8) return launch_ks<8, 512, 2>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 12) return launch_ks<12, 512, 2>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 16) return launch_ks<16, 512, 2>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 24) return launch_ks<24, 512, 2>(h, dZc, Hc, bm, nblk);
-        return launch_ks<32, 256, 2>(h, dZc, Hc, bm, nblk);
+    if (ks_direct(h)) {
+        if (Nx <= 4) return launch_ks<4, 2048, 1, false>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 8) return launch_ks<8, 2048, 1, false>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 12) return launch_ks<12, 2048, 1, false>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 16) return launch_ks<16, 2048, 1, false>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 24) return launch_ks<24, 2048, 1, false>(h, dZc, Hc, bm, nblk);
+        return launch_ks<32, 2048, 1, false>(h, dZc, Hc, bm, nblk);
     }
     if (Nx <= 4) return launch_ks<4, 512, 8>(h, dZc, Hc, bm, nblk);
     if (Nx <= 8) return launch_ks<8, 512, 8>(h, dZc, Hc, bm, nblk);

@@ -1053,7 +1053,7 @@ logdet_dot_kernel(const double* __restrict__ L, int ld, long long sL,
 // through L2 per C5 step and ran at L2 bandwidth: 85 us for ~25 us of arithmetic).
 // grid (Npad/CH, ceil(BM/HG), outputs).
 // ---------------------------------------------------------------------------------------
-template <int NXP, int CH, int HG>
+template <int NXP, int CH, int HG, bool STAGE = true>
 __global__ void __launch_bounds__(256)
 ks_rows_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
                const double* __restrict__ hyp, int hyp_ld,
@@ -1071,9 +1071,14 @@ ks_rows_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
     const int a = blockIdx.z, hg = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
     const int i0 = blk * CH;
     const double* hp = hyp + (long long)a * hyp_ld;
-    for (int idx = tid; idx < Nx * CH; idx += 256) {
-        const int d = idx / CH, r = idx - d * CH;
-        Xs[idx] = (i0 + r < ldx) ? XT[(long long)d * ldx + i0 + r] : 0.0;
+    // STAGE: the chunk of X^T is staged in shared memory and shared by the HG rows of this CTA (many outputs: L2 traffic
+    // matters).  !STAGE: X^T is read straight from global memory, one row and 2048 points (8 per thread) per CTA -- with
+    // few outputs the kernel needs long independent per-thread work between its per-row block reductions, not L2 savings
+    if (STAGE) {
+        for (int idx = tid; idx < Nx * CH; idx += 256) {
+            const int d = idx / CH, r = idx - d * CH;
+            Xs[idx] = (i0 + r < ldx) ? XT[(long long)d * ldx + i0 + r] : 0.0;
+        }
     }
     if (tid < NXP) {
         const double e = (tid < Nx) ? hp[tid] : 1.0;
@@ -1114,7 +1119,7 @@ ks_rows_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
                 for (int d = 0; d < NXP; ++d) {
                     df[d] = 0.0;
                     if (d < Nx) {
-                        df[d] = Xs[d * CH + il] - zs[r][d];
+                        df[d] = (STAGE ? Xs[d * CH + il] : XT[(long long)d * ldx + i]) - zs[r][d];
                         const double sc = df[d] * ie[d];
                         dist = fma(sc, sc, dist);
                     }
