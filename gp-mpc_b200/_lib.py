@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get('GPMPC_LIB', os.path.join(_HERE, 'lib', 'libgpmpc.so')
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NCCL, ERR_NOTPD = 0, -1, -2, -3, -4, -5
 METHOD_ME, METHOD_TA, METHOD_EM = 0, 1, 2
 GET_CHOL, GET_ALPHA, GET_INVK, GET_K, GET_LOGDET, GET_LINV, GET_ALPHA_NLML = range(7)
-PROF_KBUILD_FULL, PROF_KBUILD_LOWER, PROF_SYRK, PROF_FACTORIZE, PROF_TRIGEMM = range(5)
+PROF_KBUILD_FULL, PROF_KBUILD_LOWER, PROF_SYRK, PROF_FACTORIZE, PROF_TRIGEMM, PROF_KS, PROF_PREDICT_TAIL = range(7)
 
 # every symbol include/gpmpc.h declares: (name, restype, argtypes)
 _dp = C.POINTER(C.c_double)
@@ -52,6 +52,7 @@ SYMBOLS = [
     ('gpmpc_profile', C.c_int, [_H, C.c_int, C.c_int, C.c_int, _dp]),
     ('gpmpc_profile_balance', C.c_int, [_H, C.c_int, _dp]),
     ('gpmpc_profile_leaf', C.c_int, [_H, _dp]),
+    ('gpmpc_profile_tail', C.c_int, [_H, C.c_int, _dp]),
 ]
 
 _ll = C.c_longlong
@@ -290,6 +291,11 @@ class Engine:
         out = np.zeros(15)
         self._check(self.lib.gpmpc_profile_leaf(self.h, _ptr(out)))
         return out
+
+    def profile_tail(self, H):
+        out = np.zeros(8)
+        self._check(self.lib.gpmpc_profile_tail(self.h, int(H), _ptr(out)))
+        return dict(zip(('output_done', 'records', 'step_counter', 'staged', 'jsigma', 'written', 'kernel_span', 'tail_cta_span'), out))
 
     def profile_balance(self, H):
         out = np.zeros(4)

@@ -80,6 +80,7 @@ struct gpmpc_handle_s {
     // predict
     double *dKST = nullptr, *dPart = nullptr, *dPMJ = nullptr, *dSQ = nullptr, *dV = nullptr, *dR = nullptr, *dR2 = nullptr;
     unsigned int* dCnt = nullptr;     // stream-K counters: [nloc*nt tile | nloc output | 1 done], self-cleaning
+    int opt_ks_unroll = 2;                                  // covariance evaluations in flight per thread of the ks kernel (2 | 4)
     int psk_ctas = 0, opt_predict_ctas = 0, partCtas = 0;   // persistent grid of the predict product (2 CTAs per SM)
     double *dCovV = nullptr, *dCovOut = nullptr; long long covVcap = 0, covOutcap = 0;   // GP.covar scratch pool
     // predict_grad: U = Linv^T per output (lazy), beta rows, partial sums, per-batch derivative slabs
@@ -772,6 +773,7 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
         if (v < 0 || v > PSK_MAX_CTAS) { set_error(h, "predict_ctas must be in [0, %d]", PSK_MAX_CTAS); return GPMPC_ERR_ARG; }
         h->opt_predict_ctas = v; return GPMPC_OK;
     }
+    if (!strcmp(name, "ks_unroll")) { h->opt_ks_unroll = ((int)value == 4) ? 4 : 2; return GPMPC_OK; }
     if (!strcmp(name, "zero_copy")) { h->opt_zero_copy = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "peer_timeout_s")) { h->opt_peer_timeout_s = value > 0.0 ? value : 60.0; return GPMPC_OK; }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
@@ -903,56 +905,51 @@ static void psk_base(gpmpc_handle_t h, PredictParams& p, int Hc)
     p.hyp = h->dHyp; p.hyp_ld = h->Nx + 2; p.Nx = h->Nx;
 }
 
-// training points per CTA of the ks kernel: the chunk of X^T lives in shared memory (Nx * chunk doubles).
-// Small problems (Npad <= 4096) take 256-point chunks and 2 rows per CTA: there the kernel is latency-bound
-// and needs CTAs, not L2 savings.
-static inline bool ks_small(gpmpc_handle_t h) { return h->Npad <= 4096; }
-// large N with few local outputs: 2048-point chunks read straight from global memory, one row per CTA (see ks_rows_kernel)
-static inline bool ks_direct(gpmpc_handle_t h) { return !ks_small(h) && (long long)h->nloc * (h->Npad / 512) * 7 < 1000; }
-static inline int ks_chunk(gpmpc_handle_t h) { return ks_small(h) ? 256 : (ks_direct(h) ? 2048 : (h->Nx <= 24 ? 512 : 256)); }
+// training points per CTA of the ks kernel (ks_tile_kernel): 512-point chunks at large N (few partial blocks for the
+// finalize step to sum), 128-point chunks below 8192 so small problems still fill the machine
+static inline int ks_chunk(gpmpc_handle_t h) { return h->Npad >= 8192 ? 512 : 128; }
 
-template <int NXP, int CH, int HG, bool STAGE = true>
-static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
+template <int NXP, int CH, int UNR>
+static cudaError_t launch_ks_u(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
-    auto kern = ks_rows_kernel<NXP, CH, HG, STAGE>;
-    const int smem = STAGE ? h->Nx * CH * 8 : 0;
+    auto kern = ks_tile_kernel<NXP, CH, UNR>;
+    const int smem = (NXP + 1) * CH * 8;
     static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
     if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {      // static + dynamic may pass 48 KB
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE ? NXP * CH * 8 : 0);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         conf[h->device % GPMPC_MAX_DEVICES].store(true, std::memory_order_release);
     }
-    dim3 g(nblk, (bm + HG - 1) / HG, h->nloc);
+    dim3 g(nblk, bm / 8, h->nloc);
     kern<<<g, 256, smem, h->st>>>(h->dXT, h->Npad, h->N, h->Nx, h->dHyp, h->Nx + 2, h->dAlpha, h->Npad,
-                                  dZc, Hc, bm, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
+                                  dZc, Hc, h->dKST, h->Npad, (long long)HB * h->Npad, h->dPMJ, nblk);
     return cudaGetLastError();
 }
 
+template <int NXP, int CH>
+static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
+{
+    return h->opt_ks_unroll == 4 ? launch_ks_u<NXP, CH, 4>(h, dZc, Hc, bm, nblk) : launch_ks_u<NXP, CH, 2>(h, dZc, Hc, bm, nblk);
+}
+
+template <int CH>
+static cudaError_t launch_ks_nx(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
+{
+    const int Nx = h->Nx;       // register-array extent NXP: the next even count up to 12, then 16 / 24 / 32
+    if (Nx <= 4) return launch_ks<4, CH>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 6) return launch_ks<6, CH>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 8) return launch_ks<8, CH>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 10) return launch_ks<10, CH>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 12) return launch_ks<12, CH>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 16) return launch_ks<16, CH>(h, dZc, Hc, bm, nblk);
+    if (Nx <= 24) return launch_ks<24, CH>(h, dZc, Hc, bm, nblk);
+    return launch_ks<32, CH>(h, dZc, Hc, bm, nblk);
+}
+
+// bm = the chunk's row count rounded up to 8 (the rows of the product's A operand)
 static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
-    const int Nx = h->Nx;       // register-array extent NXP: next multiple of 4 up to 16, then 24 / 32
-    if (ks_small(h)) {
-        if (Nx <= 4) return launch_ks<4, 256, 2>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 8) return launch_ks<8, 256, 2>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 12) return launch_ks<12, 256, 2>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 16) return launch_ks<16, 256, 2>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 24) return launch_ks<24, 256, 2>(h, dZc, Hc, bm, nblk);
-        return launch_ks<32, 256, 2>(h, dZc, Hc, bm, nblk);
-    }
-    if (ks_direct(h)) {
-        if (Nx <= 4) return launch_ks<4, 2048, 1, false>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 8) return launch_ks<8, 2048, 1, false>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 12) return launch_ks<12, 2048, 1, false>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 16) return launch_ks<16, 2048, 1, false>(h, dZc, Hc, bm, nblk);
-        if (Nx <= 24) return launch_ks<24, 2048, 1, false>(h, dZc, Hc, bm, nblk);
-        return launch_ks<32, 2048, 1, false>(h, dZc, Hc, bm, nblk);
-    }
-    if (Nx <= 4) return launch_ks<4, 512, 8>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 8) return launch_ks<8, 512, 8>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 12) return launch_ks<12, 512, 8>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 16) return launch_ks<16, 512, 8>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 24) return launch_ks<24, 512, 8>(h, dZc, Hc, bm, nblk);
-    return launch_ks<32, 256, 8>(h, dZc, Hc, bm, nblk);
+    return ks_chunk(h) == 512 ? launch_ks_nx<512>(h, dZc, Hc, bm, nblk) : launch_ks_nx<128>(h, dZc, Hc, bm, nblk);
 }
 
 // rows of Amat (h-major, stride HB*np per output) times T^T with T = Li or L (lower triangular):
@@ -1010,6 +1007,10 @@ static int predict_core(gpmpc_handle_t h, int method, int H, const double* dZ, c
     // one chunk and no NCCL call in between: the product kernel's last CTA assembles too (2 launches per step)
     // (it keeps J Sigma for all H points in the pipeline's shared memory: H Ny Nx doubles, >= 68 KB available)
     const bool fused_assemble = (H <= HB) && !nccl_gather && ((long long)H * h->Ny * Nx * 8 <= 64 * 1024);
+    {   // gather records next to J Sigma in the product kernel's stage buffers (PSK_STAGES (bm + 128) 16 doubles)
+        const long long bm1 = (std::min(H, HB) + 7) / 8 * 8;
+        as.stage_g = (assemble_rows_doubles(H, h->Ny, Nx) <= (long long)PSK_STAGES * (bm1 + PSK_BN) * GEMM_BK) ? 1 : 0;
+    }
     for (int h0 = 0; h0 < H; h0 += HB) {
         const int Hc = std::min(HB, H - h0);
         const int bm = (Hc + 7) / 8 * 8;
@@ -1665,6 +1666,53 @@ extern "C" int gpmpc_profile_balance(gpmpc_handle_t h, int H, double* out4)
     return GPMPC_OK;
 }
 
+// phase stamps of the fused kernel's serial tail (the CTA that completes the step): out8 = microseconds, relative to the
+// latest end of every OTHER CTA, of {last output complete, records built, step counter passed, records staged,
+// J Sigma done, outputs written}, then the kernel's span and the tail CTA's own span.  Needs a predict call before it.
+extern "C" int gpmpc_profile_tail(gpmpc_handle_t h, int H, double* out8)
+{
+    if (!h || !out8 || H < 1 || H > HB) return GPMPC_ERR_ARG;
+    if (!h->factorized) { set_error(h, "gpmpc_profile_tail: call gpmpc_factorize first"); return GPMPC_ERR_STATE; }
+    if (h->world != 1 || h->nloc != h->Ny) { set_error(h, "gpmpc_profile_tail: single-rank handles only"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_predict_bufs(h, HB);
+    if (rc) return rc;
+    const int np = h->Npad, bm = (H + 7) / 8 * 8;
+    PredictParams p;
+    psk_base(h, p, H);
+    const int grid = psk_grid(h, p.G);
+    unsigned long long* dbg = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dbg, (size_t)(grid * 2 + 8) * 8));
+    CUDA_TRY(cudaMemset(dbg, 0, (size_t)(grid * 2 + 8) * 8));
+    p.dbg = dbg;
+    p.finalize = 1; p.PMJ = h->dPMJ; p.nblk_mj = (np + ks_chunk(h) - 1) / ks_chunk(h);
+    p.Gloc = h->dG; p.slot0 = h->a0; p.Htot = H; p.h0 = 0;
+    AssembleArgs as;
+    memset(&as, 0, sizeof(as));
+    as.G = h->dG; as.Ny = h->Ny; as.Nx = h->Nx; as.H = H; as.method_ta = 1; as.Sigma = h->dSigma;
+    as.mean = h->dMean; as.var = h->dVar; as.J = h->dJ; as.cov = h->dCov; as.world = 1;
+    as.stage_g = (assemble_rows_doubles(H, h->Ny, h->Nx) <= (long long)PSK_STAGES * (bm + PSK_BN) * GEMM_BK) ? 1 : 0;
+    as.dbg = dbg + 2 * grid;
+    p.as = as; p.do_assemble = 1;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaError_t e = psk_launch(bm, p, h->dKST, (long long)HB * np, h->dLi, slab(h), np, grid, h->st);
+        if (e != cudaSuccess) { cudaFree(dbg); set_error(h, "profile_tail: %s", cudaGetErrorString(e)); return GPMPC_ERR_CUDA; }
+    }
+    std::vector<unsigned long long> t((size_t)grid * 2 + 8);
+    cudaMemcpyAsync(t.data(), dbg, t.size() * 8, cudaMemcpyDeviceToHost, h->st);
+    cudaStreamSynchronize(h->st);
+    cudaFree(dbg);
+    unsigned long long lo = ~0ull, hi = 0, hi2 = 0; int cmax = 0;
+    for (int c = 0; c < grid; ++c) {
+        lo = std::min(lo, t[2 * c]);
+        if (t[2 * c + 1] > hi) { hi2 = hi; hi = t[2 * c + 1]; cmax = c; } else hi2 = std::max(hi2, t[2 * c + 1]);
+    }
+    for (int k = 0; k < 6; ++k) out8[k] = ((double)t[2 * grid + k] - (double)hi2) * 1e-3;
+    out8[6] = (double)(hi - lo) * 1e-3;
+    out8[7] = (double)(t[2 * cmax + 1] - t[2 * cmax]) * 1e-3;
+    return GPMPC_OK;
+}
+
 // phase clock stamps of one 128x128 leaf (potrf + trtri): out15 = clock64 at
 // {start, loaded, first panel, after block steps 1..7, L stored, inverse levels 16/32/64, Linv stored}
 extern "C" int gpmpc_profile_leaf(gpmpc_handle_t h, double* out15)
@@ -1730,10 +1778,32 @@ extern "C" int gpmpc_profile(gpmpc_handle_t h, int what, int n, int reps, double
             const int Hc = (n > 0 && n <= HB) ? n : 56;
             return tri_product(h, h->dKST, h->dLi, (Hc + 7) / 8 * 8, Hc, nullptr);
         }
+        case GPMPC_PROF_KS: {             // the ks / mean / Jacobian partial kernel alone (Z = the last batch's inputs)
+            const int Hc = (n > 0 && n <= HB) ? n : 56;
+            cudaError_t e = launch_ks_any(h, h->dZ, Hc, (Hc + 7) / 8 * 8, (np + ks_chunk(h) - 1) / ks_chunk(h));
+            if (e != cudaSuccess) { set_error(h, "profile ks: %s", cudaGetErrorString(e)); return GPMPC_ERR_CUDA; }
+            return GPMPC_OK;
+        }
+        case GPMPC_PROF_PREDICT_TAIL: {   // the fused kernel WITH finalize + assembly, without the ks kernel in front
+            const int Hc = (n > 0 && n <= HB) ? n : 56;
+            PredictParams p;
+            psk_base(h, p, Hc);
+            p.finalize = 1; p.PMJ = h->dPMJ; p.nblk_mj = (np + ks_chunk(h) - 1) / ks_chunk(h);
+            p.Gloc = h->dG; p.slot0 = h->a0; p.Htot = Hc; p.h0 = 0;
+            AssembleArgs as;
+            memset(&as, 0, sizeof(as));
+            as.G = h->dG; as.Ny = h->Ny; as.Nx = h->Nx; as.H = Hc; as.method_ta = 1; as.Sigma = h->dSigma;
+            as.mean = h->dMean; as.var = h->dVar; as.J = h->dJ; as.cov = h->dCov; as.world = 1;
+            as.stage_g = (assemble_rows_doubles(Hc, h->Ny, h->Nx) <= (long long)PSK_STAGES * ((Hc + 7) / 8 * 8 + PSK_BN) * GEMM_BK) ? 1 : 0;
+            p.as = as; p.do_assemble = (h->world == 1 && h->nloc == h->Ny) ? 1 : 0;
+            cudaError_t e = psk_launch((Hc + 7) / 8 * 8, p, h->dKST, (long long)HB * np, h->dLi, slab(h), np, psk_grid(h, p.G), h->st);
+            if (e != cudaSuccess) { set_error(h, "profile predict tail: %s", cudaGetErrorString(e)); return GPMPC_ERR_CUDA; }
+            return GPMPC_OK;
+        }
         default: set_error(h, "gpmpc_profile: unknown selector %d", what); return GPMPC_ERR_ARG;
         }
     };
-    if (what == GPMPC_PROF_TRIGEMM) { rc = ensure_predict_bufs(h, HB); if (rc) return rc; }
+    if (what == GPMPC_PROF_TRIGEMM || what == GPMPC_PROF_KS || what == GPMPC_PROF_PREDICT_TAIL) { rc = ensure_predict_bufs(h, HB); if (rc) return rc; }
     CUDA_TRY(cudaMemsetAsync(h->dJit, 0, h->nloc * sizeof(double), h->st));
     rc = run(-1);
     if (rc) return rc;
@@ -1744,6 +1814,6 @@ extern "C" int gpmpc_profile(gpmpc_handle_t h, int what, int n, int reps, double
     CUDA_TRY(cudaEventSynchronize(h->ev1));
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     ms_out[0] = (double)ms / reps;
-    if (what != GPMPC_PROF_TRIGEMM) h->factorized = false;   // slabs were used as scratch
+    if (what != GPMPC_PROF_TRIGEMM && what != GPMPC_PROF_KS && what != GPMPC_PROF_PREDICT_TAIL) h->factorized = false;   // slabs were used as scratch
     return GPMPC_OK;
 }

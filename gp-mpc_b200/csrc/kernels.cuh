@@ -1048,110 +1048,124 @@ logdet_dot_kernel(const double* __restrict__ L, int ld, long long sL,
 //   mean = ks^T alpha                  gp_functions.py:119-120,135
 //   J_d  = sum_i alpha_i ks_i (X_id - z_d)/ell_d^2   (closed form of ca.jacobian, :146-147)
 //   KST[a][h][i] (h-major) is the A operand of the v = Linv ks tensor-core product; rows h >= H are zero-filled.
-// One CTA keeps its chunk of training inputs in shared memory and loops over HG test points, so X^T is
-// read from L2 once per HG rows instead of once per row (the r1 kernel, one CTA per row, moved 587 MB
-// through L2 per C5 step and ran at L2 bandwidth: 85 us for ~25 us of arithmetic).
-// grid (Npad/CH, ceil(BM/HG), outputs).
+// One CTA = 8 test points x CH training points of one output.  A thread owns ONE test point (lane / 4) and every 32nd
+// training point of the chunk (subset 4 warp + lane % 4) for the whole loop, so the mean / Jacobian partial sums stay in
+// its registers and are reduced across lanes and warps ONCE per CTA.  (The r2 mid-round kernel looped test points per CTA
+// and ran a 13-value warp reduction per test point: ~260 instructions per covariance evaluation, 23 us at one C5 output
+// and 113 us at eight; this shape needs ~70.)  The chunk of X^T is staged in shared memory pre-scaled by 1/ell
+// (dimension-major: staging stores and the broadcast reads are both conflict-free), alpha next to it; a quarter-warp
+// reads 4 consecutive training points, a warp stores 8 rows x 32 B of KS^T per step.
+// grid (Npad/CH, BM/8, outputs); PMJ[a][h][blk][1 + Nx].
 // ---------------------------------------------------------------------------------------
-template <int NXP, int CH, int HG, bool STAGE = true>
-__global__ void __launch_bounds__(256)
-ks_rows_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
+template <int NXP, int CH, int UNR>
+__global__ void __launch_bounds__(256, (NXP <= 12 ? 2 : 1))
+ks_tile_kernel(const double* __restrict__ XT, int ldx, int N, int Nx,
                const double* __restrict__ hyp, int hyp_ld,
                const double* __restrict__ alpha, long long sal,
-               const double* __restrict__ Z, int H, int BMrows,
+               const double* __restrict__ Z, int H,
                double* __restrict__ KST, int ldk, long long sK,
                double* __restrict__ PMJ, int nblk)
 {
-    extern __shared__ double Xs[];                         // [Nx][CH]
-    __shared__ double red[8][NXP + 1];
-    __shared__ double zs[HG][NXP], ie[NXP], ie2[NXP], T16s[16], l2sf2_s;
+    extern __shared__ double sm[];                         // xs[NXP][CH] (x / ell), als[CH]
+    __shared__ double red[8][8][NXP + 1];
+    __shared__ double ie[NXP], zs[8][NXP], T32s[32], l2sf2_s;
+    double* xs = sm;
+    double* als = sm + NXP * CH;
     // let the dependent product kernel start launching once every CTA of this grid is resident (it waits
     // for this grid's completion before reading KS^T): hides its launch latency and prologue
     asm volatile("griddepcontrol.launch_dependents;");
-    const int a = blockIdx.z, hg = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+    const int a = blockIdx.z, rg = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int i0 = blk * CH;
     const double* hp = hyp + (long long)a * hyp_ld;
-    // STAGE: the chunk of X^T is staged in shared memory and shared by the HG rows of this CTA (many outputs: L2 traffic
-    // matters).  !STAGE: X^T is read straight from global memory, one row and 2048 points (8 per thread) per CTA -- with
-    // few outputs the kernel needs long independent per-thread work between its per-row block reductions, not L2 savings
-    if (STAGE) {
-        for (int idx = tid; idx < Nx * CH; idx += 256) {
-            const int d = idx / CH, r = idx - d * CH;
-            Xs[idx] = (i0 + r < ldx) ? XT[(long long)d * ldx + i0 + r] : 0.0;
-        }
+    // every global load of the prologue is issued before the first dependent instruction (in-order issue: a
+    // load -> scale -> store loop pays one L2 round trip per iteration, 20 iterations = 8 us at C5)
+    constexpr int RP = (CH + 255) / 256;
+    double xv[RP][NXP], av[RP];
+#pragma unroll
+    for (int q = 0; q < RP; ++q) {
+        const int rr = tid + 256 * q;
+        const bool in = (CH % 256 == 0 || rr < CH) && (i0 + rr < N);
+#pragma unroll
+        for (int d = 0; d < NXP; ++d) xv[q][d] = (in && d < Nx) ? XT[(long long)d * ldx + i0 + rr] : 0.0;
+        av[q] = in ? alpha[(long long)a * sal + i0 + rr] : 0.0;
     }
-    if (tid < NXP) {
-        const double e = (tid < Nx) ? hp[tid] : 1.0;
-        ie[tid] = 1.0 / e;
-        ie2[tid] = 1.0 / (e * e);
-    }
-    if (tid >= 64 && tid < 80) T16s[tid - 64] = c_exp2_tab[tid - 64];
+    if (tid < NXP) ie[tid] = (tid < Nx) ? 1.0 / hp[tid] : 0.0;
+    if (tid >= 64 && tid < 80) T32s[tid - 64] = c_exp2_tab[tid - 64];
+    else if (tid >= 80 && tid < 96) T32s[tid - 64] = c_exp2_tab2[tid - 80];
     if (tid == 96) l2sf2_s = 2.0 * log2(fabs(hp[Nx]));
-    for (int idx = tid; idx < HG * NXP; idx += 256) {
-        const int r = idx / NXP, d = idx - r * NXP, h = hg * HG + r;
-        zs[r][d] = (d < Nx && h < H) ? Z[(long long)h * Nx + d] : 0.0;
+    for (int idx = tid; idx < 8 * NXP; idx += 256) {       // Z may live in mapped host memory: one read per CTA
+        const int rr = idx / NXP, d = idx - rr * NXP, hh = rg * 8 + rr;
+        zs[rr][d] = (hh < H && d < Nx) ? Z[(long long)hh * Nx + d] : 0.0;
     }
     __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RP; ++q) {
+        const int rr = tid + 256 * q;
+        if (CH % 256 == 0 || rr < CH) {
+#pragma unroll
+            for (int d = 0; d < NXP; ++d) xs[d * CH + rr] = xv[q][d] * ie[d];
+            als[rr] = av[q];
+        }
+    }
+    const int r = lane >> 2, s = warp * 4 + (lane & 3);
+    const int h = rg * 8 + r;
+    const bool active = h < H;
+    double z[NXP], aj[NXP], am = 0.0;
+#pragma unroll
+    for (int d = 0; d < NXP; ++d) {
+        z[d] = zs[r][d] * ie[d];
+        aj[d] = 0.0;
+    }
     const double l2sf2 = l2sf2_s;
-    const double* al = alpha + (long long)a * sal;
-    double alv[CH / 256];
+    __syncthreads();
+    double* krow = KST + (long long)a * sK + (long long)h * ldk + i0;
+    if (active) {
+#pragma unroll UNR
+        for (int il = s; il < CH; il += 32) {
+            double df[NXP], d0 = 0.0, d1 = 0.0;
 #pragma unroll
-    for (int q = 0; q < CH / 256; ++q) { const int i = i0 + tid + 256 * q; alv[q] = (i < N) ? al[i] : 0.0; }
-    for (int r = 0; r < HG; ++r) {
-        const int h = hg * HG + r;
-        if (h >= BMrows) break;
-        double* krow = KST + (long long)a * sK + (long long)h * ldk;
-        if (h >= H) {                                      // padding rows of the A operand: zeros
-#pragma unroll
-            for (int q = 0; q < CH / 256; ++q) { const int i = i0 + tid + 256 * q; if (i < ldk) krow[i] = 0.0; }
-            continue;
-        }
-        double am = 0.0, aj[NXP];
-#pragma unroll
-        for (int d = 0; d < NXP; ++d) aj[d] = 0.0;
-#pragma unroll
-        for (int q = 0; q < CH / 256; ++q) {
-            const int il = tid + 256 * q, i = i0 + il;
-            double ks = 0.0;
-            if (i < N) {
-                double dist = 0.0, df[NXP];
-#pragma unroll
-                for (int d = 0; d < NXP; ++d) {
-                    df[d] = 0.0;
-                    if (d < Nx) {
-                        df[d] = (STAGE ? Xs[d * CH + il] : XT[(long long)d * ldx + i]) - zs[r][d];
-                        const double sc = df[d] * ie[d];
-                        dist = fma(sc, sc, dist);
-                    }
-                }
-                // sf2 exp(-dist/2) = 2^(log2 sf2 - log2(e)/2 dist) with the table exp2 of the K build (~2 ulp, half the
-                // instructions of the library exp)
-                double te = fma(-0.72134752044448170, dist, l2sf2);
-                te = (te < -1020.0) ? -1020.0 : te;
-                ks = exp2_t16(te, T16s);
-                const double w = alv[q] * ks;
-                am += w;
-#pragma unroll
-                for (int d = 0; d < NXP; ++d) aj[d] = fma(w, df[d], aj[d]);
+            for (int d = 0; d < NXP; d += 2) {
+                df[d] = xs[d * CH + il] - z[d];
+                df[d + 1] = xs[(d + 1) * CH + il] - z[d + 1];
+                d0 = fma(df[d], df[d], d0);
+                d1 = fma(df[d + 1], df[d + 1], d1);
             }
-            if (i < ldk) krow[i] = ks;
-        }
-        am = warp_sum(am);
+            // sf2 exp(-dist/2) = 2^(log2 sf2 - log2(e)/2 dist) with the two-level table exp2 of the K build (~2 ulp)
+            double te = fma(-0.72134752044448170, d0 + d1, l2sf2);
+            te = (te < -1020.0) ? -1020.0 : te;
+            double ks = exp2_t2lvl(te, T32s);
+            if (i0 + il >= N) ks = 0.0;
+            const double w = als[il] * ks;
+            am += w;
 #pragma unroll
-        for (int d = 0; d < NXP; ++d) aj[d] = warp_sum(aj[d]);
-        __syncthreads();                                   // red[] of the previous row has been consumed
-        if ((tid & 31) == 0) {
-            red[tid >> 5][0] = am;
+            for (int d = 0; d < NXP; ++d) aj[d] = fma(w, df[d], aj[d]);
+            if (i0 + il < ldk) krow[il] = ks;
+        }
+    } else {
+        for (int il = s; il < CH; il += 32)
+            if (i0 + il < ldk) krow[il] = 0.0;               // padding rows of the A operand: zeros
+    }
+    // one reduction per CTA: the 4 subsets of a row inside the warp, then the 8 warps through shared memory
+    am += __shfl_xor_sync(0xffffffffu, am, 1);
+    am += __shfl_xor_sync(0xffffffffu, am, 2);
 #pragma unroll
-            for (int d = 0; d < NXP; ++d) red[tid >> 5][d + 1] = aj[d];
-        }
-        __syncthreads();
-        if (tid <= Nx) {
-            double sacc = 0.0;
-            for (int q = 0; q < 8; ++q) sacc += red[q][tid];
-            if (tid > 0) sacc *= ie2[tid - 1];
-            PMJ[(((long long)a * H + h) * nblk + blk) * (Nx + 1) + tid] = sacc;
-        }
+    for (int d = 0; d < NXP; ++d) {
+        aj[d] += __shfl_xor_sync(0xffffffffu, aj[d], 1);
+        aj[d] += __shfl_xor_sync(0xffffffffu, aj[d], 2);
+    }
+    if ((lane & 3) == 0) {
+        red[warp][r][0] = am;
+#pragma unroll
+        for (int d = 0; d < NXP; ++d) red[warp][r][d + 1] = aj[d];
+    }
+    __syncthreads();
+    if (tid < 8 * (Nx + 1)) {
+        const int rr = tid / (Nx + 1), f = tid - rr * (Nx + 1), hh = rg * 8 + rr;
+        double sacc = ((red[0][rr][f] + red[1][rr][f]) + (red[2][rr][f] + red[3][rr][f])) +
+                      ((red[4][rr][f] + red[5][rr][f]) + (red[6][rr][f] + red[7][rr][f]));
+        if (f > 0) sacc *= ie[f - 1];                        // df was scaled by 1/ell: one more 1/ell makes (x - z)/ell^2
+        if (hh < H) PMJ[(((long long)a * H + hh) * nblk + blk) * (Nx + 1) + f] = sacc;
     }
 }
 

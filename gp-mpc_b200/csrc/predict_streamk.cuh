@@ -48,6 +48,8 @@ struct AssembleArgs {
     const unsigned long long* flags;  // peer mode: this step's flag row (world entries), else null
     int world; unsigned long long step; int* status;
     long long timeout_clocks;
+    unsigned long long* dbg;          // profiling: globaltimer stamps of the tail's phases (null in production)
+    int stage_g;                      // fused tail: the gather records fit the pipeline's shared memory next to J Sigma
 };
 
 struct PredictParams {
@@ -71,6 +73,11 @@ struct PredictParams {
 
 // ---- stage 5: assemble mean (H,Ny), var (H,Ny), J (H,Ny,Nx) and the covariance for test point h:
 // 'ME' diag(var) (gp_functions.py:142); 'TA' diag(var) + J Sigma J^T (build_TA_cov, :167-171).
+__device__ __forceinline__ void tail_stamp(unsigned long long* dbg, int k, int tid)
+{
+    if (dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
+}
+
 template <bool WARP>
 __device__ __forceinline__ void assemble_point(const AssembleArgs& A, int h, double* sh, int tid, int nth)
 {
@@ -115,10 +122,16 @@ __device__ __forceinline__ void assemble_point(const AssembleArgs& A, int h, dou
     if (WARP) __syncwarp(); else __syncthreads();
 }
 
-// all H points at once by one CTA (the fused tail of the product kernel): flat index spaces instead of a
-// point at a time, so the 256 threads stay busy -- phase A: outputs mean/var/J and JS = J Sigma into shared
-// memory (H Ny Nx doubles), phase B: cov.  Same arithmetic and summation order as assemble_point.
-__device__ __forceinline__ void assemble_flat(const AssembleArgs& A, double* JS, int tid, int nth)
+// all H points at once by one CTA (the fused tail of the product kernel).  One CTA at 2 warps per scheduler is
+// latency-bound -- a dependent L2 load costs ~800 cycles, a dependent fp64 op ~40 -- so the tail is organised around
+// independent work per thread:
+//   assemble_rows (stage_g: records + J Sigma fit the pipeline's shared memory): the gather records are copied to shared
+//     memory in batches of independent loads, re-laid [point][output][field] with odd strides (conflict-free); then a
+//     thread owns one (point, output) row and keeps 8 independent accumulators (8 columns of J Sigma, then 8 columns of
+//     cov): 1.3 us instead of 12.5 us for phases A + B at C5 (8 outputs), outputs are written coalesced.
+//   assemble_flat_global: the r2 mid-round flat loops straight from L2 (any size).
+// Both use the summation order of assemble_point (ascending d, then ascending e).
+__device__ __forceinline__ void assemble_flat_global(const AssembleArgs& A, double* JS, int tid, int nth)
 {
     const int Ny = A.Ny, Nx = A.Nx, H = A.H, NyNx = Ny * Nx;
     const bool ta = A.cov && A.method_ta;
@@ -154,6 +167,102 @@ __device__ __forceinline__ void assemble_flat(const AssembleArgs& A, double* JS,
             A.cov[idx] = s;
         }
     }
+}
+
+// shared-memory doubles assemble_rows needs (host side: AssembleArgs::stage_g)
+__host__ __device__ inline long long assemble_rows_doubles(int H, int Ny, int Nx)
+{
+    return (long long)H * Ny * (((Nx + 2) | 1) + (Nx | 1)) + (long long)Nx * Nx;
+}
+
+__device__ __forceinline__ void assemble_rows(const AssembleArgs& A, double* sh, int tid, int nth)
+{
+    const int Ny = A.Ny, Nx = A.Nx, H = A.H, F = Nx + 2, FP = F | 1, NP = Nx | 1, R = H * Ny;
+    const bool ta = A.cov && A.method_ta;
+    double* Gs = sh;                                   // [H Ny][FP]: mean, var, J_0.. of (point, output)
+    double* JS = Gs + R * FP;                          // [H Ny][NP]: (J Sigma) row, later the cov row
+    double* Ss = JS + R * NP;                          // [Nx][Nx]: one Sigma for every point
+    const bool sig_s = ta && !A.sigma_per_point;
+    {
+        const int tot = R * F, HF = H * F;
+        if (sig_s) for (int i = tid; i < Nx * Nx; i += nth) Ss[i] = A.Sigma[i];
+        constexpr int SB = 20;                                  // C5, 8 outputs: 4800 records words = 19 per thread
+        for (int idx = tid; idx < tot; idx += SB * nth) {      // all loads of a batch first
+            double v[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) v[k] = (idx + k * nth < tot) ? __ldcg(A.G + idx + k * nth) : 0.0;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) {
+                const int o = idx + k * nth;
+                if (o < tot) {
+                    const int a = o / HF, rem = o - a * HF, h = rem / F, q = rem - h * F;
+                    Gs[(h * Ny + a) * FP + q] = v[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    tail_stamp(A.dbg, 3, tid);
+    if (A.J) for (int i = tid; i < R * Nx; i += nth) { const int row = i / Nx; A.J[i] = Gs[row * FP + 2 + (i - row * Nx)]; }
+    for (int idx = tid; idx < R; idx += nth) {
+        const double* g = Gs + idx * FP;
+        if (A.mean) A.mean[idx] = g[0];
+        if (A.var) A.var[idx] = g[1];
+        if (ta) {
+            const int h = idx / Ny;
+            const double* Sg = sig_s ? Ss : A.Sigma + (long long)h * Nx * Nx;
+            for (int e0 = 0; e0 < Nx; e0 += 8) {
+                double acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+                for (int d = 0; d < Nx; ++d) {
+                    const double jd = g[2 + d];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) if (e0 + k < Nx) acc[k] = fma(jd, Sg[d * Nx + e0 + k], acc[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (e0 + k < Nx) JS[idx * NP + e0 + k] = acc[k];
+            }
+        }
+    }
+    __syncthreads();
+    tail_stamp(A.dbg, 4, tid);
+    if (A.cov) {
+        const bool via_smem = Ny <= 8 && Ny <= NP;        // the finished cov row replaces the thread's own J Sigma row
+        for (int idx = tid; idx < R; idx += nth) {
+            const int h = idx / Ny, a = idx - h * Ny;
+            const double var = Gs[idx * FP + 1];
+            for (int b0 = 0; b0 < Ny; b0 += 8) {
+                double acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+                if (ta) {
+                    for (int e = 0; e < Nx; ++e) {
+                        const double je = JS[idx * NP + e];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) if (b0 + k < Ny) acc[k] = fma(je, Gs[(h * Ny + b0 + k) * FP + 2 + e], acc[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (b0 + k < Ny) {
+                        const double c = ((a == b0 + k) ? var : 0.0) + acc[k];
+                        if (via_smem) JS[idx * NP + k] = c; else A.cov[(long long)idx * Ny + b0 + k] = c;
+                    }
+                }
+            }
+        }
+        if (via_smem) {
+            __syncthreads();
+            for (int i = tid; i < R * Ny; i += nth) { const int row = i / Ny; A.cov[i] = JS[row * NP + (i - row * Ny)]; }
+        }
+    }
+}
+
+__device__ __forceinline__ void assemble_flat(const AssembleArgs& A, double* sh, int tid, int nth)
+{
+    if (A.stage_g) assemble_rows(A, sh, tid, nth);
+    else assemble_flat_global(A, sh, tid, nth);
 }
 
 // peer mode: acquire every source rank's flag for this step; false = a rank never showed up
@@ -210,36 +319,65 @@ __device__ __forceinline__ void psk_iter_next(PskIter& it, int nt)
     }
 }
 
-// [mean, var, J_0..] records of output a for the chunk's test points.  Flat over (point, field): every thread owns
-// one record field at a time and sums its partials in fixed order (deterministic); one warp per point with a
-// serial loop over the partial blocks took 14 us here at one output (50 points x 32 blocks x 11 fields).
-//   mean, J from the partial sums of ks_rows_kernel; var = sf2 - sum_jt SQ (gp_functions.py:125-126,136)
+// Records [mean, var, J_0..] of (output a, test point h), built in two places:
+//   psk_reduce_mj: mean and J from the partial sums of ks_rows_kernel (gp_functions.py:119-120,135,146-147).  They do
+//     not depend on the product, so the fused kernel spreads these sums over ALL its CTAs and runs them while the first
+//     TMA stages are in flight (item = (a, h, field), one thread each, its nblk loads issued in batches of 16).
+//   psk_finalize_output: var = sf2 - sum_jt SQ (gp_functions.py:125-126,136) by the CTA that completes the output: 4 lanes
+//     per test point, each one chain of nt/4 tile sums, combined (s0+s1)+(s2+s3) by two shuffles.
+// A serial load -> add loop costs one L2 round trip (~800 cycles) per iteration on one in-order warp: the r2 mid-round
+// tail (one CTA, both jobs, divergent per-field branches) took 13.5 us at C5; the var part alone is ~1.5 us.
+__device__ __forceinline__ void psk_store_record(const PredictParams& p, int a, int h, int q, double val)
+{
+    const long long off = (((long long)(p.slot0 + a)) * p.Htot + p.h0 + h) * (p.Nx + 2) + q;
+    if (!p.use_peers) p.Gloc[off] = val;
+    else for (int r = 0; r < p.pa.world; ++r) p.pa.base[r][p.pa.goff + off] = val;
+}
+
+// items [i_begin, i_end) of the flat (a, h, field) space, field 0 = mean, 1 + d = J_d; threads [t0, t0 + nthr) of the CTA
+__device__ __forceinline__ void psk_reduce_mj(const PredictParams& p, int i_begin, int i_end, int t, int nthr)
+{
+    const int F1 = p.Nx + 1;
+    for (int i = i_begin + t; i < i_end; i += nthr) {
+        const int ah = i / F1, qq = i - ah * F1, a = ah / p.Hc, h = ah - a * p.Hc;
+        const double* pm = p.PMJ + ((long long)ah * p.nblk_mj) * F1 + qq;
+        double s0 = 0.0, s1 = 0.0;                         // even / odd blocks, fixed association
+        int b = 0;
+        for (; b + 16 <= p.nblk_mj; b += 16) {
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = __ldcg(pm + (long long)(b + k) * F1);
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) { s0 += v[k]; s1 += v[k + 1]; }
+        }
+        for (; b + 2 <= p.nblk_mj; b += 2) { s0 += __ldcg(pm + (long long)b * F1); s1 += __ldcg(pm + (long long)(b + 1) * F1); }
+        if (b < p.nblk_mj) s0 += __ldcg(pm + (long long)b * F1);
+        psk_store_record(p, a, h, qq == 0 ? 0 : qq + 1, s0 + s1);
+    }
+}
+
 __device__ __forceinline__ void psk_finalize_output(const PredictParams& p, int a, int tid, int nth)
 {
-    const int Nx = p.Nx, F = Nx + 2;
-    for (int idx = tid; idx < p.Hc * F; idx += nth) {
-        const int h = idx / F, q = idx - h * F;            // q = 0: mean, 1: var, q >= 2: J_{q-2}
-        double val;
-        if (q == 1) {
+    const int Nx = p.Nx;
+    const double sf = p.hyp[(long long)a * p.hyp_ld + Nx];
+    for (int base = 0; base < p.Hc; base += nth / 4) {         // nth is a multiple of 32
+        const int h = base + (tid >> 2), j0 = tid & 3;
+        double sj = 0.0;
+        if (h < p.Hc) {
             const double* sq = p.SQ + ((long long)a * 64 + h) * p.nt;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // four independent chains, fixed association
-            int j = 0;
-            for (; j + 4 <= p.nt; j += 4) { s0 += __ldcg(sq + j); s1 += __ldcg(sq + j + 1); s2 += __ldcg(sq + j + 2); s3 += __ldcg(sq + j + 3); }
-            for (; j < p.nt; ++j) s0 += __ldcg(sq + j);
-            const double sf = p.hyp[(long long)a * p.hyp_ld + Nx];
-            val = sf * sf - ((s0 + s1) + (s2 + s3));
-        } else {
-            const int qq = (q == 0) ? 0 : q - 1;               // PMJ field: 0 = mean, d+1 = J_d
-            const double* pm = p.PMJ + (((long long)a * p.Hc + h) * p.nblk_mj) * (Nx + 1) + qq;
-            double s0 = 0.0, s1 = 0.0;
-            int b = 0;
-            for (; b + 2 <= p.nblk_mj; b += 2) { s0 += pm[(long long)b * (Nx + 1)]; s1 += pm[(long long)(b + 1) * (Nx + 1)]; }
-            if (b < p.nblk_mj) s0 += pm[(long long)b * (Nx + 1)];
-            val = s0 + s1;
+            int j = j0;
+            for (; j + 4 * 15 < p.nt; j += 4 * 16) {
+                double v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = __ldcg(sq + j + 4 * k);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) sj += v[k];
+            }
+            for (; j < p.nt; j += 4) sj += __ldcg(sq + j);
         }
-        const long long off = (((long long)(p.slot0 + a)) * p.Htot + p.h0 + h) * F + q;
-        if (!p.use_peers) p.Gloc[off] = val;
-        else for (int r = 0; r < p.pa.world; ++r) p.pa.base[r][p.pa.goff + off] = val;
+        sj += __shfl_xor_sync(0xffffffffu, sj, 1);            // s0 + s1 | s2 + s3
+        sj += __shfl_xor_sync(0xffffffffu, sj, 2);            // (s0 + s1) + (s2 + s3)
+        if (h < p.Hc && j0 == 0) psk_store_record(p, a, h, 1, sf * sf - sj);
     }
     if (p.use_peers) __threadfence_system(); else __threadfence();
 }
@@ -265,10 +403,13 @@ __device__ __forceinline__ void psk_step_tail(const PredictParams& p, double* sh
             asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(p.pa.step) : "memory");
         }
     }
+    tail_stamp(p.as.dbg, 2, tid);
     if (p.do_assemble) {
         __threadfence();
         if (peer_acquire(p.as, tid, s_ok)) assemble_flat(p.as, sh, tid, nth);
     }
+    __syncthreads();
+    tail_stamp(p.as.dbg, 5, tid);
 }
 
 // refinement path: the solved rows were corrected outside the product (v = v1 + Li r), so the
@@ -292,6 +433,8 @@ finalize_kernel(const PredictParams p)
     extern __shared__ double sh[];
     __shared__ unsigned int s_flag;
     __shared__ int s_ok;
+    const int per = p.Hc * (p.Nx + 1);
+    psk_reduce_mj(p, blockIdx.x * per, (blockIdx.x + 1) * per, threadIdx.x, PSK_THREADS);
     psk_finalize_output(p, blockIdx.x, threadIdx.x, PSK_THREADS);
     psk_step_tail(p, sh, threadIdx.x, PSK_THREADS, &s_flag, &s_ok);
 }
@@ -367,6 +510,16 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
 #pragma unroll
         for (int s = 0; s < AHEAD; ++s)
             if (s_pg < nsteps) issue();
+    }
+    if (p.finalize) {
+        // this CTA's share of the mean / Jacobian records (warps 1..7; thread 0 is the TMA producer), while the first
+        // stages are in flight.  Ordered before the step's publication by the fence + counter chain every CTA's tiles
+        // go through (each CTA owns at least one k-step).
+        const int tot = p.nloc * p.Hc * (p.Nx + 1), per = (tot + (int)C - 1) / (int)C;
+        if (tid >= 32) {
+            psk_reduce_mj(p, min(tot, (int)c * per), min(tot, ((int)c + 1) * per), tid - 32, PSK_THREADS - 32);
+            if (p.use_peers) __threadfence_system();
+        }
     }
 
     PskIter cit;
@@ -491,7 +644,9 @@ predict_streamk_kernel(const PredictParams p, const __grid_constant__ CUtensorMa
 
         // ---- this CTA completed output a: build its records; last output => publish / assemble
         __threadfence();
+        tail_stamp(p.as.dbg, 0, tid);
         if (p.finalize) psk_finalize_output(p, a, tid, PSK_THREADS);
+        tail_stamp(p.as.dbg, 1, tid);
         psk_step_tail(p, smem, tid, PSK_THREADS, &s_flag, &s_ok);
     }
     if (p.dbg && threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); p.dbg[2 * blockIdx.x + 1] = t1; }

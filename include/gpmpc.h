@@ -59,7 +59,9 @@ enum {
     GPMPC_PROF_KBUILD_LOWER = 1,  /* covSEard K build, lower triangle only            */
     GPMPC_PROF_SYRK = 2,          /* Cholesky trailing update C -= P P^T (DMMA GEMM)  */
     GPMPC_PROF_FACTORIZE = 3,     /* potrf + trtri of one output (K prebuilt each rep) */
-    GPMPC_PROF_TRIGEMM = 4        /* predict v = Linv ks product, all local outputs    */
+    GPMPC_PROF_TRIGEMM = 4,       /* predict v = Linv ks product, all local outputs    */
+    GPMPC_PROF_KS = 5,            /* ks / partial mean / partial Jacobian kernel alone (after a predict call) */
+    GPMPC_PROF_PREDICT_TAIL = 6   /* product + finalize + assembly in one launch, no ks kernel in front (after a predict call) */
 };
 
 int gpmpc_version(void);
@@ -185,6 +187,11 @@ int gpmpc_profile(gpmpc_handle_t h, int what, int n, int reps, double* ms_out);
 /* Load balance of the persistent predict product for an H-point batch: per-CTA busy time
  * out4 = {shortest, longest, mean, first start -> last end} in microseconds (%globaltimer). */
 int gpmpc_profile_balance(gpmpc_handle_t h, int H, double* out4);
+
+/* Serial tail of the fused predict kernel (the CTA that completes the step), H-point batch, after a predict call:
+ * out8 = microseconds relative to the latest end of every other CTA of {last output complete, records built,
+ * step counter passed, records staged, J Sigma done, outputs written}, kernel span, tail CTA span. */
+int gpmpc_profile_tail(gpmpc_handle_t h, int H, double* out8);
 
 /* Phase clock stamps (SM cycles since kernel start) of one 128x128 potrf+trtri leaf: out15 =
  * {start, block loaded, first panel, block steps 1..7, L stored, inverse levels 16/32/64, L^-1 stored}. */
