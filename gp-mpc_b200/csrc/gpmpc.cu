@@ -80,7 +80,6 @@ struct gpmpc_handle_s {
     // predict
     double *dKST = nullptr, *dPart = nullptr, *dPMJ = nullptr, *dSQ = nullptr, *dV = nullptr, *dR = nullptr, *dR2 = nullptr;
     unsigned int* dCnt = nullptr;     // stream-K counters: [nloc*nt tile | nloc output | 1 done], self-cleaning
-    int opt_ks_unroll = 2;                                  // covariance evaluations in flight per thread of the ks kernel (2 | 4)
     int psk_ctas = 0, opt_predict_ctas = 0, partCtas = 0;   // persistent grid of the predict product (2 CTAs per SM)
     double *dCovV = nullptr, *dCovOut = nullptr; long long covVcap = 0, covOutcap = 0;   // GP.covar scratch pool
     // predict_grad: U = Linv^T per output (lazy), beta rows, partial sums, per-batch derivative slabs
@@ -773,7 +772,6 @@ extern "C" int gpmpc_set_option(gpmpc_handle_t h, const char* name, double value
         if (v < 0 || v > PSK_MAX_CTAS) { set_error(h, "predict_ctas must be in [0, %d]", PSK_MAX_CTAS); return GPMPC_ERR_ARG; }
         h->opt_predict_ctas = v; return GPMPC_OK;
     }
-    if (!strcmp(name, "ks_unroll")) { h->opt_ks_unroll = ((int)value == 4) ? 4 : 2; return GPMPC_OK; }
     if (!strcmp(name, "zero_copy")) { h->opt_zero_copy = value != 0.0; return GPMPC_OK; }
     if (!strcmp(name, "peer_timeout_s")) { h->opt_peer_timeout_s = value > 0.0 ? value : 60.0; return GPMPC_OK; }
     if (!strcmp(name, "gemm_variant")) { h->opt_gemm_variant = (int)value; return GPMPC_OK; }
@@ -905,14 +903,20 @@ static void psk_base(gpmpc_handle_t h, PredictParams& p, int Hc)
     p.hyp = h->dHyp; p.hyp_ld = h->Nx + 2; p.Nx = h->Nx;
 }
 
-// training points per CTA of the ks kernel (ks_tile_kernel): 512-point chunks at large N (few partial blocks for the
-// finalize step to sum), 128-point chunks below 8192 so small problems still fill the machine
-static inline int ks_chunk(gpmpc_handle_t h) { return h->Npad >= 8192 ? 512 : 128; }
-
-template <int NXP, int CH, int UNR>
-static cudaError_t launch_ks_u(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
+// training points per CTA of the ks kernel (ks_tile_kernel): 128-point chunks below N = 8192 so small problems still fill
+// the machine; 512 at large N (few partial blocks for the record sums); 1024 when a rank also holds several outputs --
+// the per-CTA prologue / epilogue (~2 us of a ~5 us CTA at 512) is then amortised over twice the evaluations, and the
+// 16 chunks x 7 row groups x outputs still cover the SMs.  (Nx <= 12: the chunk of X^T must leave room for 2 CTAs per SM.)
+static inline int ks_chunk(gpmpc_handle_t h)
 {
-    auto kern = ks_tile_kernel<NXP, CH, UNR>;
+    if (h->Npad < 8192) return 128;
+    return (h->nloc >= 2 && h->Nx <= 12) ? 1024 : 512;
+}
+
+template <int NXP, int CH>
+static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
+{
+    auto kern = ks_tile_kernel<NXP, CH, 2>;
     const int smem = (NXP + 1) * CH * 8;
     static std::atomic<bool> conf[GPMPC_MAX_DEVICES];
     if (!conf[h->device % GPMPC_MAX_DEVICES].load(std::memory_order_acquire)) {      // static + dynamic may pass 48 KB
@@ -926,12 +930,6 @@ static cudaError_t launch_ks_u(gpmpc_handle_t h, const double* dZc, int Hc, int 
     return cudaGetLastError();
 }
 
-template <int NXP, int CH>
-static cudaError_t launch_ks(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
-{
-    return h->opt_ks_unroll == 4 ? launch_ks_u<NXP, CH, 4>(h, dZc, Hc, bm, nblk) : launch_ks_u<NXP, CH, 2>(h, dZc, Hc, bm, nblk);
-}
-
 template <int CH>
 static cudaError_t launch_ks_nx(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
@@ -941,15 +939,22 @@ static cudaError_t launch_ks_nx(gpmpc_handle_t h, const double* dZc, int Hc, int
     if (Nx <= 8) return launch_ks<8, CH>(h, dZc, Hc, bm, nblk);
     if (Nx <= 10) return launch_ks<10, CH>(h, dZc, Hc, bm, nblk);
     if (Nx <= 12) return launch_ks<12, CH>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 16) return launch_ks<16, CH>(h, dZc, Hc, bm, nblk);
-    if (Nx <= 24) return launch_ks<24, CH>(h, dZc, Hc, bm, nblk);
-    return launch_ks<32, CH>(h, dZc, Hc, bm, nblk);
+    if (CH <= 512) {
+        if (Nx <= 16) return launch_ks<16, (CH <= 512 ? CH : 512)>(h, dZc, Hc, bm, nblk);
+        if (Nx <= 24) return launch_ks<24, (CH <= 512 ? CH : 512)>(h, dZc, Hc, bm, nblk);
+        return launch_ks<32, (CH <= 512 ? CH : 512)>(h, dZc, Hc, bm, nblk);
+    }
+    return cudaErrorInvalidValue;                              // ks_chunk never picks 1024 above Nx = 12
 }
 
 // bm = the chunk's row count rounded up to 8 (the rows of the product's A operand)
 static cudaError_t launch_ks_any(gpmpc_handle_t h, const double* dZc, int Hc, int bm, int nblk)
 {
-    return ks_chunk(h) == 512 ? launch_ks_nx<512>(h, dZc, Hc, bm, nblk) : launch_ks_nx<128>(h, dZc, Hc, bm, nblk);
+    switch (ks_chunk(h)) {
+    case 1024: return launch_ks_nx<1024>(h, dZc, Hc, bm, nblk);
+    case 512: return launch_ks_nx<512>(h, dZc, Hc, bm, nblk);
+    default: return launch_ks_nx<128>(h, dZc, Hc, bm, nblk);
+    }
 }
 
 // rows of Amat (h-major, stride HB*np per output) times T^T with T = Li or L (lower triangular):

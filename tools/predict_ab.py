@@ -15,10 +15,7 @@ for nout in (1, 8):
     eng = gp_mpc_b200.Engine(N, 10, nout, device=0)
     eng.set_data(w['X'], w['Y']); eng.set_hyper(w['hyper']); eng.factorize()
     eng.predict(w['Z'], w['Sigma'], L.METHOD_TA)
-    for unr in (2, 4):
-        eng.set_option('ks_unroll', unr)
-        print('N=%d H=%d outputs=%d  ks kernel alone (unroll %d) %.1f us' % (N, H, nout, unr, eng.profile(L.PROF_KS, n=H, reps=20) * 1e3), flush=True)
-    eng.set_option('ks_unroll', 2)
+    print('N=%d H=%d outputs=%d  ks kernel alone %.1f us' % (N, H, nout, eng.profile(L.PROF_KS, n=H, reps=20) * 1e3), flush=True)
     print('N=%d H=%d outputs=%d  product only %.1f us   product + finalize + assemble %.1f us' % (
         N, H, nout, eng.profile(L.PROF_TRIGEMM, n=H, reps=20) * 1e3, eng.profile(L.PROF_PREDICT_TAIL, n=H, reps=20) * 1e3), flush=True)
     print('   tail phases (us after the last other CTA ended):', {k: round(v, 1) for k, v in eng.profile_tail(H).items()}, flush=True)
