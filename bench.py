@@ -30,8 +30,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 WORKLOADS = {
     'c5': dict(N=16384, Nx=10, Ny=8, H=50, cfg=5, name='C5: N=16384 Nx=10 Ny=8 H=50 TA, outputs sharded over GPUs'),
