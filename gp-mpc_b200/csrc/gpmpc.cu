@@ -829,6 +829,8 @@ static int ensure_predict_bufs(gpmpc_handle_t h, int H)
         ALLOC(h->dG, (long long)nyp * cap * (Nx + 2));
         ALLOC(h->dIn, cap * Nx + cap * Nx * Nx);
         ALLOC(h->dOut, cap * (2 * Ny + Ny * Nx + Ny * Ny));
+        // defined contents for the profiling selectors when every call so far went through the zero-copy path
+        CUDA_TRY(cudaMemsetAsync(h->dIn, 0, (size_t)(cap * Nx + cap * Nx * Nx) * 8, h->st));
         h->dZ = h->dIn; h->dSigma = h->dIn + cap * Nx;
         h->dMean = h->dOut; h->dVar = h->dOut + cap * Ny; h->dJ = h->dOut + 2 * cap * Ny;
         h->dCov = h->dOut + 2 * cap * Ny + cap * Ny * Nx;

@@ -154,6 +154,27 @@ def test_predict_synthetic_vs_oracle(N, Nx, Ny, H):
     eng.close()
 
 
+def test_profiling_entry_points_leave_the_engine_intact():
+    """gpmpc_profile (ks / product / product + tail selectors), gpmpc_profile_balance and gpmpc_profile_tail run the
+    production kernels on the engine's own buffers: times are positive and the next predict call is bit-identical."""
+    L = _L()
+    p = orc.synthetic_problem(700, 6, 3, config_id=77, H=40)
+    eng, _ = _fit_engine(p['X'], p['Y'], p['hyper'])
+    ref = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
+    for what in (L.PROF_KS, L.PROF_TRIGEMM, L.PROF_PREDICT_TAIL):
+        ms = eng.profile(what, n=40, reps=3)
+        assert np.isfinite(ms) and ms > 0.0
+    bal = eng.profile_balance(40)
+    assert 0.0 < bal['min_us'] <= bal['max_us'] <= bal['span_us']
+    tail = eng.profile_tail(40)
+    assert tail['output_done'] <= tail['records'] <= tail['step_counter'] <= tail['staged'] <= tail['jsigma'] <= tail['written']
+    assert tail['written'] < 1e3 and tail['kernel_span'] > 0.0
+    again = eng.predict(p['Z'], p['Sigma'], L.METHOD_TA)
+    for a, b in zip(ref, again):
+        assert np.array_equal(a, b)
+    eng.close()
+
+
 def test_full_size_properties_n4096():
     """C3-size (N=4096) checks that do not need the O(N^3) CPU oracle: L Linv = I on probe
     columns, the interpolation identity Kf alpha = y - sn2 alpha at training points, var > 0."""
