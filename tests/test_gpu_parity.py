@@ -711,9 +711,11 @@ def test_parallel_per_output_fits_equal_the_sequential_loop():
 
 # ------------------------------------------------------------------ edge cases / error behaviour
 @pytest.mark.parametrize('N,Nx,Ny,H', [(1, 1, 1, 1), (2, 3, 2, 5), (127, 4, 1, 64), (128, 4, 1, 65), (129, 2, 2, 129),
-                                       (257, 32, 1, 3)])
+                                       (257, 32, 1, 3), (200, 3, 11, 9), (300, 10, 12, 64)])
 def test_edge_sizes(N, Nx, Ny, H):
-    """smallest / ragged / maximum-Nx shapes: padding to 128, H chunking at 64, Nx = NX_MAX."""
+    """smallest / ragged / maximum-Nx shapes: padding to 128, H chunking at 64, Nx = NX_MAX; more than 8 outputs (second
+    column block of the row-wise assembly), and a batch whose records do not fit the fused tail's shared memory (flat
+    assembly from L2)."""
     rng = np.random.default_rng(N * 7 + H)
     X = rng.standard_normal((N, Nx)); Y = rng.standard_normal((N, Ny))
     hyper = np.column_stack([rng.uniform(1.0, 3.0, (Ny, Nx)), np.full(Ny, 1.3), np.full(Ny, 0.05)])
