@@ -40,6 +40,7 @@ SYMBOLS = [
     ('gpmpc_get_size', C.c_int, [_H, _ip, _ip, _ip]),
     ('gpmpc_append', C.c_int, [_H, _dp, _dp]),
     ('gpmpc_posterior_cov', C.c_int, [_H, C.c_int, _dp, _dp]),
+    ('gpmpc_rollout', C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     ('gpmpc_predict_device', C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ('gpmpc_get', C.c_int, [_H, C.c_int, C.c_int, _dp]),
@@ -230,6 +231,20 @@ class Engine:
                                                ptrs['mean'], ptrs['var'], ptrs['cov'], ptrs['jac']))
             return (arrs['mean'].copy(), arrs['var'].copy(),
                     arrs['cov'].copy() if want_cov else None, arrs['jac'].copy() if want_jac else None)
+
+    def rollout(self, z0, U, Sigma0, method=METHOD_TA, scale=None):
+        """gpmpc_rollout: Nt open-loop steps with the state kept on the device.  z0:(Nx,), U:(Nt,Nu) (GP input units),
+        Sigma0:(Nx,Nx), scale:(4,Ny)|None -> means (Nt,Ny), vars (Nt,Ny), cov_last (Ny,Ny) in GP output units."""
+        Nu = self.Nx - self.Ny
+        z0 = _f64(z0, (self.Nx,)); Sigma0 = _f64(Sigma0, (self.Nx, self.Nx))
+        U = _f64(U).reshape(-1, Nu) if Nu > 0 else np.zeros((int(np.shape(U)[0]), 0))
+        Nt = U.shape[0]
+        if scale is not None:
+            scale = _f64(scale, (4, self.Ny))
+        means = np.empty((Nt, self.Ny)); var = np.empty((Nt, self.Ny)); cov = np.empty((self.Ny, self.Ny))
+        self._check(self.lib.gpmpc_rollout(self.h, int(method), Nt, _ptr(z0), _ptr(U) if Nu > 0 else None, _ptr(Sigma0),
+                                           _ptr(scale), _ptr(means), _ptr(var), _ptr(cov)))
+        return means, var, cov
 
     def predict_grad(self, Z, Sigma=None, method=METHOD_TA, want_hess=False):
         """Predict + first derivatives w.r.t. the test inputs (gpmpc_predict_grad).

@@ -85,6 +85,7 @@ struct gpmpc_handle_s {
     // predict_grad: U = Linv^T per output (lazy), beta rows, partial sums, per-batch derivative slabs
     double *dUall = nullptr, *dBeta = nullptr, *dPDV = nullptr, *dPH = nullptr, *dGradOut = nullptr; bool u_valid = false; int gradHcap = 0;
     double *dG = nullptr, *dZ = nullptr, *dSigma = nullptr, *dMean = nullptr, *dVar = nullptr, *dJ = nullptr, *dCov = nullptr;
+    double* dRoll = nullptr; size_t rollCap = 0;   // gpmpc_rollout: [Z | Sigma | U | scale | means | vars | cov]
     double *dIn = nullptr, *dOut = nullptr;   // [Z | Sigma] and [mean | var | J | cov] slabs: one H2D + one D2H per host call
     int Hcap = 0;
     double* hPinned = nullptr; double* dPinnedAlias = nullptr; size_t hPinnedBytes = 0; int opt_zero_copy = 1;
@@ -493,7 +494,7 @@ extern "C" int gpmpc_destroy(gpmpc_handle_t h)
     if (h->dCnt) cudaFree(h->dCnt);
     if (h->hPeerStatus) cudaFreeHost(h->hPeerStatus);
     double* bufs[] = {h->dXT, h->dMu, h->dY, h->dHyp, h->dHypTmp, h->dJit, h->dL, h->dLi, h->dW1, h->dW2, h->dAlpha, h->dTmp,
-                      h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dR2, h->dCovV, h->dCovOut, h->dUall, h->dBeta, h->dPDV, h->dPH, h->dGradOut, h->dG, h->dIn, h->dOut, h->dU, h->dKinv, h->dGradPart, h->dGrad,
+                      h->dRes, h->dKST, h->dPart, h->dPMJ, h->dSQ, h->dV, h->dR, h->dR2, h->dCovV, h->dCovOut, h->dUall, h->dBeta, h->dPDV, h->dPH, h->dGradOut, h->dG, h->dRoll, h->dIn, h->dOut, h->dU, h->dKinv, h->dGradPart, h->dGrad,
                       h->dEmTr, h->dEmLQ, h->dEmVec, h->dEmE2, h->dEmF2, h->dEMP, h->dEmE, h->dEmF, h->dEmW, h->dEmIJ, h->dEmMeanPart, h->dEmPart};
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->dInfo) cudaFree(h->dInfo);
@@ -1275,6 +1276,89 @@ extern "C" int gpmpc_predict_device(gpmpc_handle_t h, int method, int H, const d
     rc = predict_core(h, method, H, dZ, dSigma, spp, d_mean, d_var, d_cov, d_jac);
     if (rc) return rc;
     if (sync) CUDA_TRY(cudaStreamSynchronize(h->st));
+    return GPMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Open-loop multi-step prediction with the state kept on the device (GP.rollout = the numeric loop of
+// predict_compare, gp_class.py:746-804).  The host loop pays a call (launches + sync + copies + Python) per step
+// although a step's device work at MPC sizes is tens of microseconds; here all Nt steps are enqueued back to back:
+//   z_t = [ (mean_{t-1} sY + mY - mX) / sX , u_{t-1} ],  Sigma_t = [cov_{t-1} 0; 0 Sigma_uu]  ->  (mean_t, cov_t)
+// with the reference's operation order (gp_class.py:629-638), so the trajectory is the host loop's bit for bit.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rollout_feedback_kernel(const double* __restrict__ mean_t, const double* __restrict__ cov_t, const double* __restrict__ u_t,
+                        const double* __restrict__ scale, int Ny, int Nu, double* __restrict__ Z, double* __restrict__ Sigma)
+{
+    const int Nx = Ny + Nu, tid = threadIdx.x;
+    for (int j = tid; j < Nx; j += 256) {
+        if (j < Ny) {
+            double z = mean_t[j];
+            if (scale) {                                     // [sY | mY | mX | sX]; no fused multiply-add: numpy does not fuse
+                const double x = __dadd_rn(__dmul_rn(z, scale[j]), scale[Ny + j]);
+                z = __ddiv_rn(__dsub_rn(x, scale[2 * Ny + j]), scale[3 * Ny + j]);
+            }
+            Z[j] = z;
+        } else {
+            Z[j] = u_t[j - Ny];
+        }
+    }
+    for (int idx = tid; idx < Ny * Ny; idx += 256) {
+        const int r = idx / Ny, c = idx - r * Ny;
+        Sigma[r * Nx + c] = cov_t[idx];
+    }
+}
+
+extern "C" int gpmpc_rollout(gpmpc_handle_t h, int method, int Nt, const double* z0, const double* U, const double* Sigma0,
+                             const double* scale, double* means, double* vars, double* cov_last)
+{
+    int rc = predict_check(h, method, 1);
+    if (rc) return rc;
+    const int Nx = h->Nx, Ny = h->Ny, Nu = Nx - Ny;
+    if (method == GPMPC_METHOD_EM) { set_error(h, "gpmpc_rollout: methods ME and TA (EM prepares every point on the host)"); return GPMPC_ERR_ARG; }
+    if (Nt < 1 || !z0 || !Sigma0 || !means || !vars || (Nu > 0 && !U)) { set_error(h, "gpmpc_rollout: null argument / Nt < 1"); return GPMPC_ERR_ARG; }
+    if (Nu < 0) { set_error(h, "gpmpc_rollout: needs Nx = Ny + Nu with Nu >= 0 (Nx=%d, Ny=%d)", Nx, Ny); return GPMPC_ERR_ARG; }
+    if (h->world != 1 || h->nloc != Ny) { set_error(h, "gpmpc_rollout: all outputs must live on this handle"); return GPMPC_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    rc = ensure_predict_bufs(h, 1);
+    if (rc) return rc;
+    NvtxRange nvtx_r("gpmpc.rollout");
+    // device slab: [Z | Sigma | U | scale | means | vars | cov], host mirror in the pinned buffer
+    const size_t o_sig = Nx, o_u = o_sig + (size_t)Nx * Nx, o_sc = o_u + (size_t)Nt * Nu, o_m = o_sc + 4 * (size_t)Ny;
+    const size_t o_v = o_m + (size_t)Nt * Ny, o_c = o_v + (size_t)Nt * Ny, tot = o_c + (size_t)Nt * Ny * Ny;   // one cov per step
+    if (tot > h->rollCap) {
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (h->dRoll) cudaFree(h->dRoll);
+        h->dRoll = nullptr; h->rollCap = 0;
+        ALLOC(h->dRoll, tot);
+        h->rollCap = tot;
+    }
+    rc = ensure_pinned(h, tot * 8);
+    if (rc) return rc;
+    double* pin = h->hPinned;
+    memcpy(pin, z0, (size_t)Nx * 8);
+    memcpy(pin + o_sig, Sigma0, (size_t)Nx * Nx * 8);
+    if (Nu > 0) memcpy(pin + o_u, U, (size_t)Nt * Nu * 8);
+    if (scale) memcpy(pin + o_sc, scale, 4 * (size_t)Ny * 8);
+    CUDA_TRY(cudaMemcpyAsync(h->dRoll, pin, o_m * 8, cudaMemcpyHostToDevice, h->st));
+    double* d = h->dRoll;
+    for (int t = 0; t < Nt; ++t) {
+        double* cov_t = d + o_c + (size_t)t * Ny * Ny;
+        rc = predict_core(h, method, 1, d, d + o_sig, 0, d + o_m + (size_t)t * Ny, d + o_v + (size_t)t * Ny, cov_t, nullptr);
+        if (rc) return rc;
+        if (t + 1 < Nt) {
+            rollout_feedback_kernel<<<1, 256, 0, h->st>>>(d + o_m + (size_t)t * Ny, cov_t, d + o_u + (size_t)(t + 1) * Nu,
+                                                          scale ? d + o_sc : nullptr, Ny, Nu, d, d + o_sig);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(pin + o_m, d + o_m, (tot - o_m) * 8, cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    memcpy(means, pin + o_m, (size_t)Nt * Ny * 8);
+    // the reference records diag(covar_x) of every step (gp_class.py:793): the propagated variance, JSigmaJ^T included
+    for (int t = 0; t < Nt; ++t)
+        for (int a = 0; a < Ny; ++a) vars[(size_t)t * Ny + a] = pin[o_c + (size_t)t * Ny * Ny + (size_t)a * Ny + a];
+    if (cov_last) memcpy(cov_last, pin + o_c + (size_t)(Nt - 1) * Ny * Ny, (size_t)Ny * Ny * 8);
     return GPMPC_OK;
 }
 

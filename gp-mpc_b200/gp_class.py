@@ -392,7 +392,7 @@ class GP:
                                      None if cov is None else np.asarray(cov, dtype=np.float64))
         return mean.reshape(self.__Ny, 1), c[0]
 
-    def rollout(self, x0, u, methods=None):
+    def rollout(self, x0, u, methods=None, device_rollout=True):
         """ The numeric multi-step prediction of ``predict_compare`` (reference
         gp_class.py:746-804, open-loop branch) without the plotting / plant simulation:
         for every method, propagate (mean, covariance) through ``predict`` over the input
@@ -400,7 +400,8 @@ class GP:
         Returns mean, var of shape (len(methods), Nt+1, Ny); var is rescaled by stdY^2 when
         normalize (:795-796)."""
         Nx, Ny = self.__Nx, self.__Ny
-        u = np.asarray(u, dtype=np.float64).reshape(-1, self.__Nu)
+        u = np.asarray(u, dtype=np.float64)
+        u = u.reshape(-1, self.__Nu) if self.__Nu > 0 else np.zeros((u.shape[0] if u.ndim else 0, 0))   # Nu = 0: Nt = len(u)
         Nt = u.shape[0]
         initVar = self.__hyper[:, Nx + 1] ** 2
         if methods is None:                             # gp_class.py:747 default; 'EM' only where it can run
@@ -410,11 +411,28 @@ class GP:
         var = np.zeros((len(methods), Nt + 1, Ny))
         covar = np.eye(Nx) * 1e-6                       # shared across methods, as in the reference
         keep = self.__gp_method
+        # 'ME' / 'TA' on a single handle: all Nt steps run on the device (gpmpc_rollout), same arithmetic as the loop below
+        on_device = (device_rollout and hasattr(self.__engine, 'rollout') and self.__comm.world == 1
+                     and not (self.__prior_mean_in_predict and self.__has_prior_mean()))
         for i, meth in enumerate(methods):
             self.set_method(meth)
             mean_t = np.asarray(x0, dtype=np.float64).reshape(-1)
             covar[:Ny, :Ny] = np.diag(initVar)
             mean[i, 0, :] = mean_t
+            if on_device and meth in ('ME', 'TA') and Nt > 0:
+                un = u
+                z_x = mean_t
+                scale = None
+                if self.__normalize:
+                    z_x = self.standardize(mean_t, self.__meanX, self.__stdX)
+                    un = self.standardize(u, self.__meanU, self.__stdU)
+                    scale = np.stack([self.__stdY, self.__meanY, self.__meanX, self.__stdX])
+                z0 = np.concatenate([np.asarray(z_x, dtype=np.float64).reshape(-1), un[0].reshape(-1)])
+                m_std, v_std, c_last = self.__engine.rollout(z0, un, covar, _GPU_METHODS[meth], scale)
+                mean[i, 1:, :] = self.inverse_mean(m_std, self.__meanY, self.__stdY) if self.__normalize else m_std
+                var[i, 1:, :] = self.inverse_variance(v_std) if self.__normalize else v_std
+                covar[:Ny, :Ny] = c_last
+                continue
             for t in range(1, Nt + 1):
                 mean_t, covar_x = self.predict(mean_t, u[t - 1, :], covar)
                 mean_t = np.array(mean_t).reshape(Ny)

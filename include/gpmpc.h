@@ -142,6 +142,20 @@ int gpmpc_predict_grad(gpmpc_handle_t h, int method, int H, const double* Z, con
                        int sigma_per_point, double* mean, double* var, double* cov, double* jac,
                        double* dvar_dz, double* dcov_dz, double* hess);
 
+/* Open-loop multi-step prediction with the state kept on the device: the numeric loop of GP.predict_compare
+ * (gp_class.py:746-804, :779-792: mean_t, covar_x = predict(mean_t, u_t, covar); covar[:Ny,:Ny] = covar_x) for a
+ * model whose inputs are z = [x, u] (Nx = Ny + Nu).  All Nt steps are enqueued back to back, one synchronisation.
+ *   z0      (Nx)        first input [x_0, u_0], already in the GP's input units (standardised when the GP normalises)
+ *   U       (Nt, Nu)    inputs u_0 .. u_{Nt-1}, GP input units (row 0 repeats z0's tail); may be NULL when Nu = 0
+ *   Sigma0  (Nx, Nx)    covariance of z0; afterwards only its top-left Ny x Ny block is replaced by cov_t
+ *   scale   (4, Ny)     [stdY | meanY | meanX | stdX] or NULL: next x = ((mean * stdY + meanY) - meanX) / stdX, the
+ *                       inverse_mean / standardize pair of gp_class.py:629-638 in the same operation order
+ *   means, vars (Nt, Ny) predicted means / diag(cov_t) (the propagated variance the reference records, gp_class.py:793)
+ *                       in the GP's output units, cov_last (Ny, Ny) or NULL
+ * method GPMPC_METHOD_ME or _TA; the handle must own all outputs. */
+int gpmpc_rollout(gpmpc_handle_t h, int method, int Nt, const double* z0, const double* U, const double* Sigma0,
+                  const double* scale, double* means, double* vars, double* cov_last);
+
 /* Problem sizes of a handle (GP.get_size, gp_class.py:266-274: N, and Nx, Ny). */
 int gpmpc_get_size(gpmpc_handle_t h, int* N, int* Nx, int* Ny);
 

@@ -642,7 +642,7 @@ def test_gp_class_validate_and_io(tmp_path):
         assert relinf(mb[h], mh.ravel()) < 1e-12 and relinf(cb[h], ch) < 1e-12
     # sequential roll-out (numeric part of predict_compare, gp_class.py:777-804) vs the oracle loop
     useq = np.tile(d['u0'], (6, 1)) * (1 + 0.02 * np.arange(6)[:, None])
-    rm, rv = gp.rollout(d['x0'], useq, methods=['TA', 'ME'])
+    rm, rv = gp.rollout(d['x0'], useq, methods=['TA', 'ME'], device_rollout=False)      # one host call per step
     for i, meth in enumerate(['TA', 'ME']):
         cv = np.eye(6) * 1e-6; cv[:4, :4] = np.diag(m['hyper'][:, 7] ** 2); xt = d['x0'].copy()
         for t in range(6):
@@ -794,6 +794,38 @@ def test_autonomous_system_nu_zero_rollout():
         mo, co = orc.predict(model, xo, np.zeros(0), np.zeros((2, 2)), 'ME')
         assert relinf(mean, mo) < TOL and relinf(np.diag(cov), np.diag(co)) < TOL
         x = np.array(mean).flatten(); xo = mo.flatten()
+    gp.close()
+
+
+@pytest.mark.parametrize('name', ['tank', 'car'])
+def test_device_rollout_equals_the_host_loop(name):
+    """gpmpc_rollout (all steps enqueued on the device, state fed back by a kernel) against GP.rollout's host loop
+    (one predict call per step, gp_class.py:777-804): same operation order, so the trajectories agree to rounding."""
+    gp, m = _gp_from_fixture(name)
+    d = load_golden('derived', name)
+    useq = np.tile(d['u0'], (12, 1)) * (1 + 0.02 * np.arange(12)[:, None])
+    rm, rv = gp.rollout(d['x0'], useq, methods=['TA', 'ME'])
+    rm_h, rv_h = gp.rollout(d['x0'], useq, methods=['TA', 'ME'], device_rollout=False)
+    assert rm.shape == rm_h.shape and relinf(rm, rm_h) < 1e-12 and relinf(rv, rv_h) < 1e-12
+    assert (rv[:, 1:] > 0).all()
+    gp.close()
+
+
+def test_device_rollout_autonomous_system():
+    """Nu = 0 (van_der_pol.py): 25 'ME' steps on the device equal 25 sequential GP.predict calls."""
+    import gp_mpc_b200
+    rng = np.random.default_rng(12)
+    X = rng.uniform(-2, 2, (40, 2))
+    Y = np.column_stack([X[:, 0] + 0.1 * X[:, 1], X[:, 1] + 0.1 * (-X[:, 0] + (1 - X[:, 0] ** 2) * X[:, 1])])
+    Y = Y + 2e-2 * rng.standard_normal(Y.shape)
+    hyper = np.column_stack([np.full((2, 2), 1.5), np.full(2, 1.2), np.full(2, 0.05)])
+    gp = gp_mpc_b200.GP(X, Y, normalize=True, xlb=[-2, -2], xub=[2, 2], ulb=[], uub=[], gp_method='ME', hyper=dict(hyper=hyper))
+    x = np.array([1.0, 0.5]); traj = []
+    for t in range(25):
+        mean, cov = gp.predict(x, [], np.zeros((2, 2)))
+        x = np.array(mean).flatten(); traj.append(x.copy())
+    rm, rv = gp.rollout(np.array([1.0, 0.5]), np.zeros((25, 0)), methods=['ME'])
+    assert rm.shape == (1, 26, 2) and relinf(rm[0, 1:], np.array(traj)) < 1e-12 and (rv[0, 1:] > 0).all()
     gp.close()
 
 
