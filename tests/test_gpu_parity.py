@@ -819,7 +819,7 @@ def test_device_rollout_autonomous_system():
     Y = np.column_stack([X[:, 0] + 0.1 * X[:, 1], X[:, 1] + 0.1 * (-X[:, 0] + (1 - X[:, 0] ** 2) * X[:, 1])])
     Y = Y + 2e-2 * rng.standard_normal(Y.shape)
     hyper = np.column_stack([np.full((2, 2), 1.5), np.full(2, 1.2), np.full(2, 0.05)])
-    gp = gp_mpc_b200.GP(X, Y, normalize=True, xlb=[-2, -2], xub=[2, 2], ulb=[], uub=[], gp_method='ME', hyper=dict(hyper=hyper))
+    gp = gp_mpc_b200.GP(X, Y, normalize=False, gp_method='ME', hyper=dict(hyper=hyper))
     x = np.array([1.0, 0.5]); traj = []
     for t in range(25):
         mean, cov = gp.predict(x, [], np.zeros((2, 2)))
