@@ -84,3 +84,27 @@ class OracleEngine:
 
     def close(self):
         self.closed = True
+
+
+class OracleEngineWithRollout(OracleEngine):
+    """Adds a numpy restatement of gpmpc_rollout (include/gpmpc.h): the feedback arithmetic of
+    rollout_feedback_kernel in the same operation order, the predict step from the oracle."""
+
+    def rollout(self, z0, U, Sigma0, method=1, scale=None):
+        Ny, Nx = self.Ny, self.Nx
+        Nu = Nx - Ny
+        U = np.asarray(U, dtype=np.float64).reshape(-1, Nu) if Nu > 0 else np.zeros((np.shape(U)[0], 0))
+        Nt = U.shape[0]
+        z = np.asarray(z0, dtype=np.float64).copy(); Sg = np.asarray(Sigma0, dtype=np.float64).copy()
+        means = np.empty((Nt, Ny)); var = np.empty((Nt, Ny)); cov = None
+        for t in range(Nt):
+            m, v, cov, _ = self.predict(z.reshape(1, -1), Sg, method, True, False)
+            means[t] = m[0]; var[t] = np.diag(cov[0])
+            if t + 1 < Nt:
+                zx = m[0]
+                if scale is not None:
+                    zx = ((zx * scale[0] + scale[1]) - scale[2]) / scale[3]
+                z = np.concatenate([zx, U[t + 1]])
+                Sg[:Ny, :Ny] = cov[0]
+        return means, var, cov[0]
+

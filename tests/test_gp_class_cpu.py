@@ -8,7 +8,7 @@ import pytest
 
 import gp_mpc_b200
 from oracle import gp_oracle as orc
-from tests._fake_engine import OracleEngine
+from tests._fake_engine import OracleEngine, OracleEngineWithRollout
 from tests._util import load_fixture, load_golden, relinf
 
 
@@ -96,7 +96,7 @@ def test_prior_mean_functions_follow_the_reference():
     and with it under the flag.  Host logic only: the engine is the oracle-backed stand-in."""
     import gp_mpc_b200
     from gp_mpc_b200 import mean_functions as mf
-    from tests._fake_engine import OracleEngine
+    from tests._fake_engine import OracleEngine, OracleEngineWithRollout
     rng = np.random.default_rng(2)
     p = orc.synthetic_problem(30, 3, 2, config_id=21, H=5)
     Nx = 3
@@ -134,3 +134,21 @@ def test_prior_mean_functions_follow_the_reference():
         mf.count_mean_params('cubic', 3)
     lbub = mf.mean_bounds(np.array([-1.0, -3.0]), 3, 'linear')                   # inverted reference interval is sorted
     assert (lbub[:, 0] <= lbub[:, 1]).all() and lbub.shape == (4, 2)
+
+
+@pytest.mark.parametrize('name', ['tank', 'car'])
+def test_rollout_device_mapping_equals_the_host_loop(name):
+    """GP.rollout hands gpmpc_rollout the standardised start / inputs and the [stdY, meanY, meanX, stdX] map; with an
+    engine that restates the C entry in numpy the device path must reproduce the per-step host loop
+    (gp_class.py:777-804) to rounding, for both methods, and the default-engine fallback (no `rollout`) is the loop."""
+    gp, m = _gp(name, engine_factory=OracleEngineWithRollout)
+    d = load_golden('derived', name)
+    useq = np.tile(d['u0'], (7, 1)) * (1 + 0.03 * np.arange(7)[:, None])
+    rm, rv = gp.rollout(d['x0'], useq, methods=['TA', 'ME'])
+    rm_h, rv_h = gp.rollout(d['x0'], useq, methods=['TA', 'ME'], device_rollout=False)
+    assert rm.shape == (2, 8, m['Y'].shape[1])
+    assert relinf(rm, rm_h) < 1e-12 and relinf(rv, rv_h) < 1e-12
+    gp2, _ = _gp(name)                                   # stand-in engine without a rollout entry: host loop
+    rm2, rv2 = gp2.rollout(d['x0'], useq, methods=['TA', 'ME'])
+    assert np.array_equal(rm2, rm_h) and np.array_equal(rv2, rv_h)
+
