@@ -36,6 +36,9 @@ def _worker(rank, world, port, case, q):
         info = dict(rank=rank, begin=eng.out_begin, count=eng.out_count, uid_ok=(eng.uid == b'u' * 128) if case == 'outputs' else True)
         mean, cov = gp.predict_batch(p['Z'][:, :Ny], p['Z'][:, Ny:], p['Sigma'])
         chol = gp.get_chol()
+        # sequential roll-out across ranks: one collective predict per step (the device-resident path needs all outputs on
+        # one handle, so sharded models keep the host loop); default methods drop 'EM' when outputs are sharded
+        roll = gp.rollout(p['Z'][0, :Ny], np.tile(p['Z'][:1, Ny:], (4, 1)), methods=['TA', 'ME'])
         # training path: every rank fits its own outputs, rows are gathered
         gp2 = gp_mpc_b200.GP(p['X'], p['Y'], normalize=False, engine_factory=OracleEngine,
                              optimizer_opts={'maxiter': 30})
@@ -59,6 +62,7 @@ def _worker(rank, world, port, case, q):
                 extra['em'] = 'accepted'
             except NotImplementedError:
                 extra['em'] = 'rejected'
+        extra['roll'] = roll
         info.update(extra)
         q.put((rank, info, mean, cov, chol, hy))
     finally:
@@ -93,6 +97,15 @@ def test_two_ranks(case):
         np.testing.assert_allclose(r[3], co, rtol=1e-9, atol=1e-14)
         np.testing.assert_allclose(r[4], post['chol'], rtol=1e-12, atol=1e-14)
     np.testing.assert_array_equal(res[0][5], res[1][5])                     # gathered hypers identical
+    # the roll-out of the sharded / point-split model equals the single-process one
+    import gp_mpc_b200
+    from tests._fake_engine import OracleEngine
+    Ny = p['Y'].shape[1]
+    gp1 = gp_mpc_b200.GP(p['X'], p['Y'], hyper=dict(hyper=p['hyper']), normalize=False, engine_factory=OracleEngine)
+    rm1, rv1 = gp1.rollout(p['Z'][0, :Ny], np.tile(p['Z'][:1, Ny:], (4, 1)), methods=['TA', 'ME'])
+    for r in res:
+        np.testing.assert_allclose(r[1]['roll'][0], rm1, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(r[1]['roll'][1], rv1, rtol=1e-9, atol=1e-14)
     assert res[0][5].shape == (p['Y'].shape[1], p['X'].shape[1] + 2)
     # and equal to what one process fits (rank-local fits are independent per output)
     for a in range(p['Y'].shape[1]):
